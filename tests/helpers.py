@@ -1,0 +1,46 @@
+"""Shared problem builders for the tests (the notebook variants are defined inline in the
+reference's notebooks, not in problems/*.jl)."""
+import numpy as np
+
+import trajopt_b200 as to
+from trajopt_b200 import api, problems
+
+
+def acrobot_notebook():
+    """examples/acrobot/Acrobot.ipynb cells 5-17"""
+    p = problems.acrobot(N=251, dt=0.01, Qs=1e-3, Rs=1e-3, Qfs=1000.0)
+    il = api.iLQRSolverOptions(cost_tolerance=1e-6)
+    al = api.AugmentedLagrangianSolverOptions(opts_uncon=il, iterations=30, penalty_scaling=10.0, cost_tolerance=1e-6,
+                                              cost_tolerance_intermediate=1e-5, constraint_tolerance=1e-4)
+    return p, al
+
+
+def car_escape_notebook():
+    """examples/car/Car Escape.ipynb cells 3-23: trap at every k<N, no bounds, R_inf=1e-3."""
+    model = api.rk3(api.Dynamics.car)
+    n, m, N, tf = 3, 2, 101, 3.0
+    x0, xf = np.array([2.5, 2.5, 0.0]), np.array([7.5, 2.5, 0.0])
+    obj = api.LQRObjective(1e-3 * np.eye(n), 1e-2 * np.eye(m), 100 * np.eye(n), xf, N)
+    cons = api.Constraints(N)
+    trap = api.CircleConstraints(problems.escape_circles(), "trap")
+    for k in range(N - 1):
+        cons.add(k, trap)
+    cons.add(N - 1, api.goal_constraint(xf))
+    Xg = [[2.5, 2.5, 0.0], [4.0, 5.0, 0.785], [5.0, 6.25, 0.0], [7.5, 6.25, -0.261], [9, 5.0, -1.57], [7.5, 2.5, 0.0]]
+    X0 = problems.natural_spline_rows(N, tf, Xg)
+    p = api.Problem(model, obj, constraints=cons, x0=x0, xf=xf, N=N, tf=tf, U0=np.ones((N - 1, m)), X0=X0)
+    al = api.AugmentedLagrangianSolverOptions(cost_tolerance=1e-4, cost_tolerance_intermediate=1e-2,
+                                              constraint_tolerance=1e-3, penalty_scaling=50.0, penalty_initial=10.0)
+    return p, api.ALTROSolverOptions(opts_al=al, R_inf=1e-3)
+
+
+def printed_close(value, printed, extra_rel=0.0):
+    """True if `value` rounds to the printed string (allowing one unit in the last printed digit
+    plus an optional relative slack for late-iteration drift)."""
+    s = printed.lower()
+    ref = float(s)
+    mant = s.split("e")[0]
+    decimals = len(mant.split(".")[1]) if "." in mant else 0
+    expo = int(s.split("e")[1]) if "e" in s else 0
+    ulp = 10.0 ** (expo - decimals)
+    return abs(value - ref) <= 1.01 * ulp + extra_rel * abs(ref)
