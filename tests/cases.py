@@ -1,0 +1,123 @@
+"""The parity cases: BASELINE.json's configs at sizes the CPU oracle finishes in seconds.
+Each entry returns (problem, options, x0[B,n], X0 or None)."""
+import numpy as np
+
+from trajopt_b200 import api, problems
+from helpers import acrobot_notebook, car_escape_notebook
+
+
+def _di(B):
+    p = problems.doubleintegrator()
+    return p, api.ALTROSolverOptions(), np.broadcast_to(p.x0, (B, 2)).copy(), None
+
+
+def _pend_ilqr(B):
+    p = problems.pendulum(N=101, dt=0.045, constrained=False)
+    return p, api.iLQRSolverOptions(), problems.batch_x0("pendulum", B), None
+
+
+def _cart_ilqr(B):
+    p = problems.cartpole(constrained=False)
+    return p, api.iLQRSolverOptions(), problems.batch_x0("cartpole", B), None
+
+
+def _cart_altro(B):
+    p = problems.cartpole(constrained=True)
+    return p, api.ALTROSolverOptions(), problems.batch_x0("cartpole", B), None
+
+
+def _pend_altro(B):
+    p = problems.pendulum()
+    return p, api.ALTROSolverOptions(), problems.batch_x0("pendulum", B) * 0.2, None
+
+
+def _quad(B):
+    p = problems.quadrotor()
+    return p, problems.quadrotor_bench_options(), problems.batch_x0("quadrotor", B), None
+
+
+def _quad_ilqr(B):
+    p = problems.quadrotor()
+    return p, api.iLQRSolverOptions(), problems.batch_x0("quadrotor", B), None
+
+
+def _acrobot_al(B):
+    p, al = acrobot_notebook()
+    x0 = problems.batch_x0("acrobot", B)
+    x0[0] = 0.0
+    return p, al, x0, None
+
+
+def _dp_ilqr(B):
+    p = problems.doublependulum()
+    return p, api.iLQRSolverOptions(), problems.batch_x0("doublependulum", B), None
+
+
+def escape_options():
+    """examples/IROS_2019/car_escape.jl:12-32 with projected Newton off"""
+    al = api.AugmentedLagrangianSolverOptions(cost_tolerance=1e-6, cost_tolerance_intermediate=1e-2,
+                                              constraint_tolerance=1e-3, penalty_scaling=50.0, penalty_initial=10.0)
+    return api.ALTROSolverOptions(opts_al=al, R_inf=0.1, resolve_feasible_problem=False)
+
+
+def _escape(B):
+    p = problems.car_escape()
+    x0 = problems.batch_x0("car_escape", B)
+    x0[0] = p.x0
+    X0 = np.broadcast_to(p.X, (B,) + p.X.shape).copy()
+    X0[:, 0, :] = x0
+    return p, escape_options(), x0, X0
+
+
+def _escape_notebook(B):
+    p, o = car_escape_notebook()
+    x0 = np.broadcast_to(p.x0, (B, 3)).copy()
+    X0 = np.broadcast_to(p.X, (B,) + p.X.shape).copy()
+    return p, o, x0, X0
+
+
+def park_options():
+    """benchmark/car_benchmarks.jl:18-30 with projected Newton off"""
+    al = api.AugmentedLagrangianSolverOptions(iterations=30, penalty_scaling=10.0, constraint_tolerance=1e-3)
+    return api.ALTROSolverOptions(opts_al=al)
+
+
+def _park_inf(B):
+    p = problems.parallel_park(infeasible=True)
+    x0 = problems.batch_x0("parallel_park", B)
+    x0[0] = 0.0
+    X0 = np.stack([problems.line_trajectory(x0[b], p.xf, p.N) for b in range(B)])
+    return p, park_options(), x0, X0
+
+
+def _park(B):
+    p = problems.parallel_park(infeasible=False)
+    x0 = problems.batch_x0("parallel_park", B)
+    return p, park_options(), x0, None
+
+
+def _pend_mintime(B):
+    """test/minimum_time_tests.jl:17-19,38-46 (pendulum, R_minimum_time=15, dt_max=0.15)"""
+    p = problems.pendulum()
+    p.tf = 0.0
+    al = api.AugmentedLagrangianSolverOptions(iterations=50, penalty_scaling=10.0)
+    o = api.ALTROSolverOptions(opts_al=al, R_minimum_time=15.0, dt_max=0.15, dt_min=1e-3)
+    return p, o, np.broadcast_to(p.x0, (B, 2)).copy() + 0.05 * problems.batch_x0("pendulum", B), None
+
+
+CASES = {
+    "di_altro": _di,
+    "pend_ilqr": _pend_ilqr,
+    "cart_ilqr": _cart_ilqr,
+    "pend_altro": _pend_altro,
+    "cart_altro": _cart_altro,
+    "quad_ilqr": _quad_ilqr,
+    "quad_altro": _quad,
+    "acrobot_al": _acrobot_al,
+    "dp_ilqr": _dp_ilqr,
+    "escape_altro": _escape,
+    "escape_notebook": _escape_notebook,
+    "park_altro": _park,
+    "park_inf_altro": _park_inf,
+    "pend_mintime": _pend_mintime,
+}

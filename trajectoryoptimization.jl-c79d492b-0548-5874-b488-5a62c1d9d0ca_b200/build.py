@@ -1,0 +1,104 @@
+"""Build csrc/libtrajopt_b200.so with nvcc for sm_100a (cross-compiles without a GPU).
+
+One translation unit per kernel instantiation (model × integrator × ALTRO transform) so they
+compile in parallel; `registry.cu` is generated from the same list.  Flags: -fmad=false keeps the
+arithmetic contract (FMAs only where fma() is written), -lineinfo lets ncu map SASS to source.
+"""
+import concurrent.futures as cf
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+GEN = os.path.join(CSRC, "_gen")
+LIB = os.path.join(CSRC, "libtrajopt_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+# (model, integrator, infeasible, min_time, partials per lane)
+INSTANCES = [
+    (0, 0, 0, 0, 3),
+    (1, 0, 0, 0, 3), (1, 0, 0, 1, 4),
+    (2, 0, 0, 0, 5), (2, 0, 1, 0, 5), (2, 0, 0, 1, 6), (2, 1, 0, 0, 5),
+    (3, 0, 0, 0, 5),
+    (4, 0, 0, 0, 2), (4, 1, 0, 0, 2),
+    (5, 0, 0, 0, 5), (5, 0, 0, 1, 6),
+    (6, 0, 0, 0, 6), (6, 0, 0, 1, 7),
+]
+
+
+def _name(i):
+    return "m%d_i%d_f%d_t%d" % i[:4]
+
+
+def _write(path, text):
+    if not os.path.exists(path) or open(path).read() != text:
+        open(path, "w").write(text)
+    return path
+
+
+def generate():
+    os.makedirs(GEN, exist_ok=True)
+    files = []
+    for inst in INSTANCES:
+        mo, ig, inf, mt, pc = inst
+        src = ('#include "../engine.cuh"\nnamespace tob {\nKernelInfo tob_info_%s() { return make_info<Cfg<%d, %d, %s, %s, %d>>(); }\n}\n'
+               % (_name(inst), mo, ig, "true" if inf else "false", "true" if mt else "false", pc))
+        files.append(_write(os.path.join(GEN, "inst_%s.cu" % _name(inst)), src))
+    reg = ['#include <vector>\n#include "../engine_host.h"\nnamespace tob {']
+    reg += ["KernelInfo tob_info_%s();" % _name(i) for i in INSTANCES]
+    reg.append("const KernelInfo* find_kernel(int model, int integ, int inf, int mt) {")
+    reg.append("    static const std::vector<KernelInfo> all = {%s};" % ", ".join("tob_info_%s()" % _name(i) for i in INSTANCES))
+    reg.append("    for (const auto& k : all) if (k.model == model && k.integ == integ && k.inf == inf && k.mt == mt) return &k;")
+    reg.append("    return nullptr;\n}")
+    reg.append("void model_dims(int model, int* n, int* m) {")
+    reg.append("    static const int d[7][2] = {{2, 1}, {2, 1}, {3, 2}, {4, 1}, {13, 4}, {4, 1}, {4, 2}};")
+    reg.append("    *n = d[model][0]; *m = d[model][1];\n}\n}")
+    files.append(_write(os.path.join(GEN, "registry.cu"), "\n".join(reg) + "\n"))
+    files.append(os.path.join(CSRC, "capi.cu"))
+    return files
+
+
+def _deps_hash():
+    h = hashlib.sha1()
+    for f in ("engine.cuh", "engine_host.h", "models.cuh", "capi.cu", "../build.py", "../../include/trajopt_b200.h"):
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    return h.hexdigest()
+
+
+def _compile(src):
+    obj = os.path.join(GEN, os.path.basename(src).replace(".cu", ".o"))
+    cmd = [NVCC] + ARCH + FLAGS + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return src, obj, r.returncode, r.stdout + r.stderr
+
+
+def build(force=False, verbose=False, jobs=None):
+    files = generate()
+    stamp = os.path.join(GEN, "stamp")
+    hsh = _deps_hash()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == hsh:
+        return LIB
+    jobs = jobs or max(1, (os.cpu_count() or 4))
+    objs, logs = [], []
+    with cf.ThreadPoolExecutor(jobs) as ex:
+        for src, obj, rc, out in ex.map(_compile, files):
+            logs.append("== %s\n%s" % (os.path.basename(src), out))
+            if rc != 0:
+                sys.stderr.write(out)
+                raise RuntimeError("nvcc failed on %s" % src)
+            objs.append(obj)
+    open(os.path.join(GEN, "ptxas.log"), "w").write("\n".join(logs))
+    if verbose:
+        print("\n".join(logs))
+    cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+    subprocess.check_call(cmd)
+    open(stamp, "w").write(hsh)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,628 @@
+// C ABI of include/trajopt_b200.h: host-side orchestration (descriptor validation, the ALTRO
+// problem transforms of altro_methods.jl:98-124 / infeasible.jl:2-34 / minimum_time.jl:2-37 expressed
+// as descriptor rewrites, device memory, kernel launches).  All numerics run in engine.cuh kernels;
+// nothing here computes on the CPU and there is no fallback path.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/trajopt_b200.h"
+#include "engine_host.h"
+
+using namespace tob;
+
+namespace {
+
+std::string g_create_error;
+
+#define CK_RET(s, call)                                                                            \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "CUDA error '%s' at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return (s)->fail(TO_ERR_CUDA, buf_);                                                   \
+        }                                                                                          \
+    } while (0)
+
+struct HostRow { int kind, eq, col; double sign, a, b, c, r; };
+
+// device buffers of one (cfg) variant of the problem
+struct Variant {
+    bool built = false;
+    int inf = 0, mt = 0;
+    const KernelInfo* ki = nullptr;
+    DevProblem P{};
+    std::vector<void*> allocs;
+    int grid = 0;
+    unsigned long long ws_stride = 0;
+    double* ws = nullptr;
+    double key[6] = {0, 0, 0, 0, 0, 0};  // ALTRO parameters the variant was built with
+};
+
+}  // namespace
+
+struct TOSolver {
+    int device = 0;
+    int B = 0;
+    // descriptor copy
+    TOProblemDesc d{};
+    std::vector<double> Q, R, H, q, r, Qf, qf;
+    std::vector<int32_t> class_of_knot, class_row_start;
+    std::vector<TOConstraintRow> rows;
+    // device batch
+    double *x0 = nullptr, *U0 = nullptr, *X0 = nullptr, *X = nullptr, *U = nullptr, *dts = nullptr;
+    bool has_X0 = false, batch_set = false;
+    TOResult* res = nullptr;
+    TOIterRecord* inner = nullptr;
+    TOOuterRecord* outer = nullptr;
+    int *n_inner = nullptr, *n_outer = nullptr;
+    int inner_cap = 0, outer_cap = 0;
+    double *lam_out = nullptr, *mu_out = nullptr;
+    uint8_t* act_out = nullptr;
+    int dual_P = 0;
+    unsigned int* queue = nullptr;
+    double* debug = nullptr;
+    size_t debug_doubles = 0;
+    Variant var[3];  // 0 plain, 1 infeasible, 2 minimum time
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int launches = 0;
+    int sm_count = 0;
+    int blocks_per_sm_override = 0;
+    std::string err;
+
+    int fail(int code, const std::string& msg) {
+        err = msg;
+        return code;
+    }
+};
+
+namespace {
+
+int fail_create(int code, const std::string& msg) {
+    g_create_error = msg;
+    return code;
+}
+
+bool is_diag(const std::vector<double>& M, int n) {
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++)
+            if (i != j && M[(size_t)j * n + i] != 0.0) return false;
+    return true;
+}
+bool is_zero(const std::vector<double>& M) {
+    for (double v : M) if (v != 0.0) return false;
+    return true;
+}
+
+template <class T>
+int upload(TOSolver* s, Variant& v, const std::vector<T>& h, const T** out) {
+    T* p = nullptr;
+    size_t bytes = std::max<size_t>(1, h.size()) * sizeof(T);
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return s->fail(TO_ERR_NOMEM, "cudaMalloc failed (problem data)");
+    if (!h.empty() && cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess)
+        return s->fail(TO_ERR_CUDA, "cudaMemcpy failed (problem data)");
+    v.allocs.push_back(p);
+    *out = p;
+    return 0;
+}
+
+void free_variant(Variant& v) {
+    for (void* p : v.allocs) cudaFree(p);
+    v.allocs.clear();
+    if (v.ws) cudaFree(v.ws);
+    v.ws = nullptr;
+    v.built = false;
+}
+
+// Build the (possibly ALTRO-transformed) device problem.  Row ordering follows the reference:
+// infeasible: (non-bound rows, bounds, :infeasible)           constraint_sets.jl:135-150, infeasible.jl:19-29
+// min time:   (non-bound rows, combined bound incl. sqrt(dt) bounds, :min_time_eq for 1<k<N)   minimum_time.jl:126-147
+int build_variant(TOSolver* s, int which, const TOALTROOptions* ao) {
+    Variant& v = s->var[which];
+    const bool inf = (which == 1), mt = (which == 2);
+    double key[6] = {inf ? ao->R_inf : 0.0, mt ? ao->R_minimum_time : 0.0, mt ? ao->dt_max : 0.0, mt ? ao->dt_min : 0.0, 0, 0};
+    if (v.built && memcmp(key, v.key, sizeof key) == 0) return 0;
+    free_variant(v);
+    memcpy(v.key, key, sizeof key);
+    v.inf = inf; v.mt = mt;
+    const TOProblemDesc& D = s->d;
+    v.ki = find_kernel(D.model, D.integrator, inf, mt);
+    if (!v.ki) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "no sm_100a kernel instantiated for model=%d integrator=%d infeasible=%d min_time=%d", D.model,
+                 D.integrator, (int)inf, (int)mt);
+        return s->fail(TO_ERR_UNSUPPORTED, buf);
+    }
+    const int n0 = D.n, m0 = D.m, N = D.N;
+    const int nq = n0, mq = m0 + (inf ? n0 : 0);
+    const int nbar = n0 + (mt ? 1 : 0), mbar = mq + (mt ? 1 : 0);
+    std::vector<double> R((size_t)mq * mq, 0.0), rr(mq, 0.0), H((size_t)mq * nq, 0.0);
+    for (int j = 0; j < m0; j++) for (int i = 0; i < m0; i++) R[(size_t)j * mq + i] = s->R[(size_t)j * m0 + i];
+    for (int i = 0; i < m0; i++) rr[i] = s->r[i];
+    for (int j = 0; j < n0; j++) for (int i = 0; i < m0; i++) H[(size_t)j * mq + i] = s->H[(size_t)j * m0 + i];
+    if (inf) {
+        const double rinf = (ao->R_inf * 1.0) / D.dt;  // infeasible.jl:11
+        for (int i = 0; i < n0; i++) R[(size_t)(m0 + i) * mq + (m0 + i)] = rinf;
+    }
+    DevProblem& P = v.P;
+    P.N = N; P.dt = D.dt; P.R_mt = mt ? ao->R_minimum_time : 0.0; P.c = D.c; P.cf = D.cf;
+    P.q_diag = is_diag(s->Q, n0); P.r_diag = is_diag(R, mq); P.h_zero = is_zero(H); P.qf_diag = is_diag(s->Qf, n0);
+    int rc;
+    if ((rc = upload(s, v, s->Q, &P.Q))) return rc;
+    if ((rc = upload(s, v, R, &P.R))) return rc;
+    if ((rc = upload(s, v, H, &P.H))) return rc;
+    if ((rc = upload(s, v, s->q, &P.q))) return rc;
+    if ((rc = upload(s, v, rr, &P.r))) return rc;
+    if ((rc = upload(s, v, s->Qf, &P.Qf))) return rc;
+    if ((rc = upload(s, v, s->qf, &P.qf))) return rc;
+    // rows per knot (expanded; identical knots share storage through the class table)
+    std::vector<DevRow> rows;
+    std::vector<int> kb(N), kc(N), lo(N + 1);
+    // cache per (class, position-kind) to keep the row table small: kind 0 = first knot, 1 = interior, 2 = terminal
+    struct Key { int cls, pos; int begin, count; };
+    std::vector<Key> cache;
+    int off = 0;
+    for (int k = 0; k < N; k++) {
+        const bool term = (k == N - 1);
+        const int cls = (D.n_classes > 0) ? s->class_of_knot[k] : -1;
+        const int pos = term ? 2 : ((k == 0) ? 0 : 1);
+        int found = -1;
+        for (size_t i = 0; i < cache.size(); i++) if (cache[i].cls == cls && cache[i].pos == pos) found = (int)i;
+        if (found < 0) {
+            std::vector<DevRow> nonb, bxmax, bumax, bxmin, bumin, out;
+            if (cls >= 0)
+                for (int i = s->class_row_start[cls]; i < s->class_row_start[cls + 1]; i++) {
+                    const TOConstraintRow& cr = s->rows[i];
+                    DevRow r{};
+                    r.kind = cr.kind; r.eq = cr.equality != 0; r.sign = cr.sign; r.a = cr.a; r.b = cr.b; r.c = cr.c; r.r = cr.r;
+                    r.col = cr.var;
+                    bool isx = true;
+                    if (cr.kind == TO_ROW_LINEAR) {
+                        isx = cr.var < n0;
+                        r.col = isx ? cr.var : (cr.var - n0) + nbar;
+                    }
+                    if (!inf && !mt) { out.push_back(r); continue; }
+                    if (cr.is_bound && cr.kind == TO_ROW_LINEAR) {
+                        if (cr.sign > 0) (isx ? bxmax : bumax).push_back(r);
+                        else (isx ? bxmin : bumin).push_back(r);
+                    } else {
+                        nonb.push_back(r);
+                    }
+                }
+            if (inf || mt) {
+                out = nonb;
+                auto lin = [&](int col, double sign, double a, int eq) {
+                    DevRow r{};
+                    r.kind = DR_LIN; r.eq = eq; r.col = col; r.sign = sign; r.a = a;
+                    return r;
+                };
+                out.insert(out.end(), bxmax.begin(), bxmax.end());
+                if (!term) {
+                    out.insert(out.end(), bumax.begin(), bumax.end());
+                    if (mt) out.push_back(lin(nbar + mbar - 1, 1.0, std::sqrt(ao->dt_max), 0));
+                }
+                out.insert(out.end(), bxmin.begin(), bxmin.end());
+                if (!term) {
+                    out.insert(out.end(), bumin.begin(), bumin.end());
+                    if (mt) out.push_back(lin(nbar + mbar - 1, -1.0, std::sqrt(ao->dt_min), 0));
+                }
+                if (inf && !term)
+                    for (int i = 0; i < n0; i++) out.push_back(lin(nbar + m0 + i, 1.0, 0.0, 1));
+                if (mt && k > 0 && !term) {
+                    DevRow r{};
+                    r.kind = DR_MTEQ; r.eq = 1; r.sign = 1.0;
+                    out.push_back(r);
+                }
+            }
+            Key key2{cls, pos, (int)rows.size(), (int)out.size()};
+            rows.insert(rows.end(), out.begin(), out.end());
+            cache.push_back(key2);
+            found = (int)cache.size() - 1;
+        }
+        kb[k] = cache[found].begin;
+        kc[k] = cache[found].count;
+        lo[k] = off;
+        off += kc[k];
+    }
+    lo[N] = off;
+    P.Ptot = off;
+    if ((rc = upload(s, v, rows, &P.rows))) return rc;
+    if ((rc = upload(s, v, kb, &P.knot_row_begin))) return rc;
+    if ((rc = upload(s, v, kc, &P.knot_row_count))) return rc;
+    if ((rc = upload(s, v, lo, &P.knot_lam_off))) return rc;
+    // grid + workspace
+    int per_sm = s->blocks_per_sm_override > 0 ? s->blocks_per_sm_override : v.ki->max_blocks_per_sm();
+    if (per_sm < 1) return s->fail(TO_ERR_CUDA, "kernel cannot be resident (occupancy 0)");
+    long long grid = (long long)s->sm_count * per_sm;
+    if (grid > s->B) grid = s->B;
+    v.grid = (int)grid;
+    v.ws_stride = v.ki->ws_doubles(N, P.Ptot);
+    size_t bytes = (size_t)v.grid * v.ws_stride * sizeof(double);
+    if (cudaMalloc(&v.ws, bytes) != cudaSuccess) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "cudaMalloc of %.1f MB workspace failed", bytes / 1048576.0);
+        return s->fail(TO_ERR_NOMEM, buf);
+    }
+    v.built = true;
+    return 0;
+}
+
+bool constrained(const TOSolver* s) {
+    const TOProblemDesc& D = s->d;
+    if (D.n_classes <= 0) return false;
+    for (int k = 0; k < D.N; k++) {
+        int c = s->class_of_knot[k];
+        if (c >= 0 && s->class_row_start[c + 1] > s->class_row_start[c]) return true;
+    }
+    return false;
+}
+
+int ensure_dual_buffers(TOSolver* s, int P) {
+    if (s->inner_cap <= 0 && s->outer_cap <= 0) { s->dual_P = 0; return 0; }  // only in diagnostic (trace) mode
+    if (P == s->dual_P && s->lam_out) return 0;
+    if (s->lam_out) { cudaFree(s->lam_out); cudaFree(s->mu_out); cudaFree(s->act_out); s->lam_out = s->mu_out = nullptr; s->act_out = nullptr; }
+    s->dual_P = P;
+    if (P == 0) return 0;
+    size_t cnt = (size_t)s->B * P;
+    if (cudaMalloc(&s->lam_out, cnt * 8) != cudaSuccess || cudaMalloc(&s->mu_out, cnt * 8) != cudaSuccess ||
+        cudaMalloc(&s->act_out, cnt) != cudaSuccess)
+        return s->fail(TO_ERR_NOMEM, "cudaMalloc failed (dual buffers)");
+    cudaMemsetAsync(s->lam_out, 0, cnt * 8, s->stream);
+    cudaMemsetAsync(s->mu_out, 0, cnt * 8, s->stream);
+    cudaMemsetAsync(s->act_out, 0, cnt, s->stream);
+    return 0;
+}
+
+// enqueue one kernel over the whole batch
+int launch(TOSolver* s, int which, int mode, const TOALOptions& alo, bool altro_init, bool projection_first, bool accumulate,
+           const double* X0_in, const double* U0_in) {
+    Variant& v = s->var[which];
+    DevBatch Bt{};
+    Bt.B = s->B; Bt.n_out = s->d.n; Bt.m_out = s->d.m;
+    Bt.x0 = s->x0; Bt.U0 = U0_in; Bt.X0 = X0_in;
+    Bt.X = s->X; Bt.U = s->U; Bt.dts = s->dts; Bt.res = s->res;
+    Bt.inner = s->inner; Bt.n_inner = s->n_inner; Bt.inner_cap = s->inner_cap;
+    Bt.outer = s->outer; Bt.n_outer = s->n_outer; Bt.outer_cap = s->outer_cap;
+    int rc = ensure_dual_buffers(s, mode == 1 ? v.P.Ptot : 0);
+    if (rc) return rc;
+    Bt.lam_out = (mode == 1) ? s->lam_out : nullptr; Bt.mu_out = s->mu_out; Bt.act_out = s->act_out;
+    DevCtl c{};
+    c.mode = mode; c.altro_init = altro_init; c.projection_first = projection_first; c.accumulate = accumulate;
+    c.write_solution = 1;
+    c.o = alo;
+    c.queue = s->queue;
+    c.ws = v.ws; c.ws_stride = v.ws_stride;
+    c.debug_flag = nullptr;
+    c.debug = nullptr;
+    if (s->debug_doubles > 0 && !accumulate) {
+        size_t need = v.ki->debug_doubles(s->d.N);
+        if (need <= s->debug_doubles) c.debug = s->debug;
+    }
+    CK_RET(s, cudaMemsetAsync(s->queue, 0, sizeof(unsigned int), s->stream));
+    v.ki->launch(v.grid, s->stream, v.P, Bt, c);
+    CK_RET(s, cudaGetLastError());
+    s->launches += 1;
+    return 0;
+}
+
+int check_opts(TOSolver* s, const TOALOptions& o) {
+    const TOiLQROptions& io = o.opts_uncon;
+    if (io.iterations_linesearch < 0 || io.iterations_linesearch > 31)
+        return s->fail(TO_ERR_UNSUPPORTED, "iterations_linesearch must be in [0,31] (one warp lane per step size)");
+    if (io.square_root) return s->fail(TO_ERR_UNSUPPORTED, "square_root backward pass is not built into this library yet");
+    if (!s->batch_set) return s->fail(TO_ERR_INVALID, "to_set_batch has not been called");
+    return 0;
+}
+
+int solve_common(TOSolver* s, int api_mode, const TOALTROOptions& ao, bool sync) {
+    CK_RET(s, cudaSetDevice(s->device));
+    int rc = check_opts(s, ao.opts_al);
+    if (rc) return rc;
+    const TOALOptions& alo = ao.opts_al;
+    s->launches = 0;
+    const bool con = constrained(s);
+    const double* X0_in = s->has_X0 ? s->X0 : nullptr;
+    CK_RET(s, cudaEventRecord(s->ev0, s->stream));
+    if (api_mode == 0) {
+        if ((rc = build_variant(s, 0, &ao))) return rc;
+        if ((rc = launch(s, 0, 0, alo, false, false, false, X0_in, s->U0))) return rc;
+    } else if (api_mode == 1) {
+        if ((rc = build_variant(s, 0, &ao))) return rc;
+        if ((rc = launch(s, 0, con ? 1 : 0, alo, false, false, false, X0_in, s->U0))) return rc;
+    } else {
+        const bool inf = s->has_X0;          // altro_methods.jl:102
+        const bool mt = (s->d.tf == 0.0);    // altro_methods.jl:111
+        if (inf && mt) return s->fail(TO_ERR_UNSUPPORTED, "infeasible start combined with minimum time is not supported yet");
+        const int which = inf ? 1 : (mt ? 2 : 0);
+        if ((rc = build_variant(s, which, &ao))) return rc;
+        if ((rc = launch(s, which, 1, alo, true, false, false, X0_in, s->U0))) return rc;
+        if (inf && ao.resolve_feasible_problem) {
+            // infeasible_to_feasible_problem + projection! + second AL solve (altro_methods.jl:67-78)
+            if ((rc = build_variant(s, 0, &ao))) return rc;
+            if ((rc = launch(s, 0, con ? 1 : 0, alo, false, ao.dynamically_feasible_projection != 0, true, s->X, s->U))) return rc;
+        }
+    }
+    CK_RET(s, cudaEventRecord(s->ev1, s->stream));
+    if (sync) CK_RET(s, cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+}  // namespace
+
+// ==========================================================================================
+extern "C" {
+
+void to_default_ilqr_options(TOiLQROptions* o) {
+    o->cost_tolerance = 1e-4; o->gradient_norm_tolerance = 1e-5; o->iterations = 300; o->dJ_counter_limit = 10;
+    o->square_root = 0; o->iterations_linesearch = 20; o->line_search_lower_bound = 1e-8; o->line_search_upper_bound = 10.0;
+    o->bp_reg_increase_factor = 1.6; o->bp_reg_max = 1e8; o->bp_reg_min = 1e-8; o->bp_reg_fp = 10.0;
+    o->max_cost_value = 1e8; o->max_state_value = 1e8; o->max_control_value = 1e8;
+}
+void to_default_al_options(TOALOptions* o) {
+    to_default_ilqr_options(&o->opts_uncon);
+    o->cost_tolerance = 1e-4; o->cost_tolerance_intermediate = 1e-3; o->gradient_norm_tolerance = 1e-5;
+    o->gradient_norm_tolerance_intermediate = 1e-5; o->constraint_tolerance = 1e-3; o->iterations = 30;
+    o->kickout_max_penalty = 0; o->dual_min = -1e8; o->dual_max = 1e8; o->penalty_max = 1e8; o->penalty_initial = 1.0;
+    o->penalty_scaling = 10.0;
+}
+void to_default_altro_options(TOALTROOptions* o) {
+    to_default_al_options(&o->opts_al);
+    o->R_inf = 1.0; o->dynamically_feasible_projection = 1; o->resolve_feasible_problem = 1;
+    o->R_minimum_time = 1.0; o->dt_max = 1.0; o->dt_min = 1e-3;
+}
+
+int to_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+const char* to_version(void) { return "trajopt_b200 0.1 (sm_100a, FP64, warp-resident iLQR/AL/ALTRO)"; }
+
+const char* to_last_error(TOHandle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int to_create(const TOProblemDesc* desc, int32_t B, int32_t device, TOHandle* out) {
+    if (!desc || !out || B <= 0) return fail_create(TO_ERR_INVALID, "to_create: bad arguments");
+    if (desc->model < 0 || desc->model >= TO_NUM_MODELS) return fail_create(TO_ERR_UNSUPPORTED, "unknown model id");
+    int mn, mm;
+    model_dims(desc->model, &mn, &mm);
+    if (desc->n != mn || desc->m != mm) return fail_create(TO_ERR_INVALID, "n/m do not match the model");
+    if (desc->N < 2) return fail_create(TO_ERR_INVALID, "N must be >= 2");
+    if (!(desc->dt > 0)) return fail_create(TO_ERR_INVALID, "dt must be strictly positive");  // problem.jl:66-68
+    if (!find_kernel(desc->model, desc->integrator, 0, 0)) return fail_create(TO_ERR_UNSUPPORTED, "no kernel for this model/integrator");
+    int ndev = to_device_count();
+    if (ndev <= 0) return fail_create(TO_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail_create(TO_ERR_INVALID, "device index out of range");
+    if (cudaSetDevice(device) != cudaSuccess) return fail_create(TO_ERR_CUDA, "cudaSetDevice failed");
+    TOSolver* s = new TOSolver();
+    s->device = device;
+    s->B = B;
+    s->d = *desc;
+    const int n = desc->n, m = desc->m, N = desc->N;
+    s->Q.assign(desc->Q, desc->Q + (size_t)n * n);
+    s->R.assign(desc->R, desc->R + (size_t)m * m);
+    if (desc->H) s->H.assign(desc->H, desc->H + (size_t)m * n); else s->H.assign((size_t)m * n, 0.0);
+    s->q.assign(desc->q, desc->q + n);
+    s->r.assign(desc->r, desc->r + m);
+    s->Qf.assign(desc->Qf, desc->Qf + (size_t)n * n);
+    s->qf.assign(desc->qf, desc->qf + n);
+    if (desc->n_classes > 0) {
+        s->class_of_knot.assign(desc->class_of_knot, desc->class_of_knot + N);
+        s->class_row_start.assign(desc->class_row_start, desc->class_row_start + desc->n_classes + 1);
+        s->rows.assign(desc->rows, desc->rows + s->class_row_start[desc->n_classes]);
+        for (int k = 0; k < N; k++)
+            if (s->class_of_knot[k] >= desc->n_classes) { delete s; return fail_create(TO_ERR_INVALID, "class_of_knot out of range"); }
+        for (auto& r : s->rows) {
+            if (r.kind < 0 || r.kind > TO_ROW_SPHERE) { delete s; return fail_create(TO_ERR_INVALID, "unknown constraint row kind"); }
+            if (r.kind == TO_ROW_LINEAR && (r.var < 0 || r.var >= n + m)) { delete s; return fail_create(TO_ERR_INVALID, "constraint row var out of range"); }
+            if (r.kind == TO_ROW_SPHERE && n < 3) { delete s; return fail_create(TO_ERR_INVALID, "sphere rows need n >= 3"); }
+        }
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    s->sm_count = prop.multiProcessorCount;
+    const char* env = getenv("TRAJOPT_B200_BLOCKS_PER_SM");
+    if (env) s->blocks_per_sm_override = atoi(env);
+    bool ok = true;
+    ok &= cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok &= cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess;
+    ok &= cudaMalloc(&s->x0, (size_t)B * n * 8) == cudaSuccess;
+    ok &= cudaMalloc(&s->U0, (size_t)B * (N - 1) * m * 8) == cudaSuccess;
+    ok &= cudaMalloc(&s->X, (size_t)B * N * n * 8) == cudaSuccess;
+    ok &= cudaMalloc(&s->U, (size_t)B * (N - 1) * m * 8) == cudaSuccess;
+    ok &= cudaMalloc(&s->dts, (size_t)B * (N - 1) * 8) == cudaSuccess;
+    ok &= cudaMalloc(&s->res, (size_t)B * sizeof(TOResult)) == cudaSuccess;
+    ok &= cudaMalloc(&s->queue, 256) == cudaSuccess;
+    if (!ok) { to_destroy(s); return fail_create(TO_ERR_NOMEM, "device allocation failed in to_create"); }
+    cudaMemset(s->res, 0, (size_t)B * sizeof(TOResult));
+    *out = s;
+    return 0;
+}
+
+void to_destroy(TOHandle s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (auto& v : s->var) free_variant(v);
+    void* ptrs[] = {s->x0, s->U0, s->X0, s->X, s->U, s->dts, s->res, s->inner, s->outer, s->n_inner, s->n_outer,
+                    s->lam_out, s->mu_out, s->act_out, s->queue, s->debug};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+static int set_batch_impl(TOHandle s, const double* x0, const double* U0, const double* X0, cudaMemcpyKind kind) {
+    if (!s || !x0 || !U0) return s ? s->fail(TO_ERR_INVALID, "to_set_batch: null pointer") : TO_ERR_INVALID;
+    CK_RET(s, cudaSetDevice(s->device));
+    const int n = s->d.n, m = s->d.m, N = s->d.N, B = s->B;
+    CK_RET(s, cudaMemcpyAsync(s->x0, x0, (size_t)B * n * 8, kind, s->stream));
+    CK_RET(s, cudaMemcpyAsync(s->U0, U0, (size_t)B * (N - 1) * m * 8, kind, s->stream));
+    if (X0) {
+        if (!s->X0) CK_RET(s, cudaMalloc(&s->X0, (size_t)B * N * n * 8));
+        CK_RET(s, cudaMemcpyAsync(s->X0, X0, (size_t)B * N * n * 8, kind, s->stream));
+        s->has_X0 = true;
+    } else {
+        s->has_X0 = false;
+    }
+    s->batch_set = true;
+    return 0;
+}
+int to_set_batch(TOHandle s, const double* x0, const double* U0, const double* X0) {
+    return set_batch_impl(s, x0, U0, X0, cudaMemcpyHostToDevice);
+}
+int to_set_batch_device(TOHandle s, const double* x0, const double* U0, const double* X0) {
+    return set_batch_impl(s, x0, U0, X0, cudaMemcpyDeviceToDevice);
+}
+
+int to_set_trace(TOHandle s, int32_t inner_capacity, int32_t outer_capacity) {
+    if (!s || inner_capacity < 0 || outer_capacity < 0) return TO_ERR_INVALID;
+    CK_RET(s, cudaSetDevice(s->device));
+    if (s->inner) { cudaFree(s->inner); cudaFree(s->n_inner); s->inner = nullptr; s->n_inner = nullptr; }
+    if (s->outer) { cudaFree(s->outer); cudaFree(s->n_outer); s->outer = nullptr; s->n_outer = nullptr; }
+    s->inner_cap = inner_capacity;
+    s->outer_cap = outer_capacity;
+    if (inner_capacity > 0) {
+        CK_RET(s, cudaMalloc(&s->inner, (size_t)s->B * inner_capacity * sizeof(TOIterRecord)));
+        CK_RET(s, cudaMalloc(&s->n_inner, (size_t)s->B * 4));
+        CK_RET(s, cudaMemset(s->n_inner, 0, (size_t)s->B * 4));
+    }
+    if (outer_capacity > 0) {
+        CK_RET(s, cudaMalloc(&s->outer, (size_t)s->B * outer_capacity * sizeof(TOOuterRecord)));
+        CK_RET(s, cudaMalloc(&s->n_outer, (size_t)s->B * 4));
+        CK_RET(s, cudaMemset(s->n_outer, 0, (size_t)s->B * 4));
+    }
+    return 0;
+}
+
+int to_solve_ilqr(TOHandle s, const TOiLQROptions* o) {
+    if (!s || !o) return TO_ERR_INVALID;
+    TOALTROOptions ao;
+    to_default_altro_options(&ao);
+    ao.opts_al.opts_uncon = *o;
+    return solve_common(s, 0, ao, true);
+}
+int to_solve_al(TOHandle s, const TOALOptions* o) {
+    if (!s || !o) return TO_ERR_INVALID;
+    TOALTROOptions ao;
+    to_default_altro_options(&ao);
+    ao.opts_al = *o;
+    return solve_common(s, 1, ao, true);
+}
+int to_solve_altro(TOHandle s, const TOALTROOptions* o) {
+    if (!s || !o) return TO_ERR_INVALID;
+    return solve_common(s, 2, *o, true);
+}
+int to_solve_altro_async(TOHandle s, const TOALTROOptions* o) {
+    if (!s || !o) return TO_ERR_INVALID;
+    return solve_common(s, 2, *o, false);
+}
+int to_sync(TOHandle s) {
+    if (!s) return TO_ERR_INVALID;
+    CK_RET(s, cudaSetDevice(s->device));
+    CK_RET(s, cudaStreamSynchronize(s->stream));
+    return 0;
+}
+int to_last_kernel_ms(TOHandle s, float* ms) {
+    if (!s || !ms) return TO_ERR_INVALID;
+    CK_RET(s, cudaEventSynchronize(s->ev1));
+    CK_RET(s, cudaEventElapsedTime(ms, s->ev0, s->ev1));
+    return 0;
+}
+int to_last_launch_count(TOHandle s, int32_t* count) {
+    if (!s || !count) return TO_ERR_INVALID;
+    *count = s->launches;
+    return 0;
+}
+
+int to_get_solution(TOHandle s, double* X, double* U, double* dts) {
+    if (!s) return TO_ERR_INVALID;
+    CK_RET(s, cudaSetDevice(s->device));
+    const int n = s->d.n, m = s->d.m, N = s->d.N, B = s->B;
+    if (X) CK_RET(s, cudaMemcpyAsync(X, s->X, (size_t)B * N * n * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (U) CK_RET(s, cudaMemcpyAsync(U, s->U, (size_t)B * (N - 1) * m * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (dts) CK_RET(s, cudaMemcpyAsync(dts, s->dts, (size_t)B * (N - 1) * 8, cudaMemcpyDeviceToHost, s->stream));
+    CK_RET(s, cudaStreamSynchronize(s->stream));
+    return 0;
+}
+int to_get_results(TOHandle s, TOResult* results) {
+    if (!s || !results) return TO_ERR_INVALID;
+    CK_RET(s, cudaSetDevice(s->device));
+    CK_RET(s, cudaMemcpyAsync(results, s->res, (size_t)s->B * sizeof(TOResult), cudaMemcpyDeviceToHost, s->stream));
+    CK_RET(s, cudaStreamSynchronize(s->stream));
+    return 0;
+}
+int to_results_device_ptr(TOHandle s, void** ptr) {
+    if (!s || !ptr) return TO_ERR_INVALID;
+    *ptr = s->res;
+    return 0;
+}
+int to_get_trace(TOHandle s, TOIterRecord* inner, int32_t* n_inner, TOOuterRecord* outer, int32_t* n_outer) {
+    if (!s) return TO_ERR_INVALID;
+    CK_RET(s, cudaSetDevice(s->device));
+    CK_RET(s, cudaStreamSynchronize(s->stream));
+    if (s->inner_cap > 0 && inner && n_inner) {
+        CK_RET(s, cudaMemcpy(inner, s->inner, (size_t)s->B * s->inner_cap * sizeof(TOIterRecord), cudaMemcpyDeviceToHost));
+        CK_RET(s, cudaMemcpy(n_inner, s->n_inner, (size_t)s->B * 4, cudaMemcpyDeviceToHost));
+    } else if (n_inner) {
+        memset(n_inner, 0, (size_t)s->B * 4);
+    }
+    if (s->outer_cap > 0 && outer && n_outer) {
+        CK_RET(s, cudaMemcpy(outer, s->outer, (size_t)s->B * s->outer_cap * sizeof(TOOuterRecord), cudaMemcpyDeviceToHost));
+        CK_RET(s, cudaMemcpy(n_outer, s->n_outer, (size_t)s->B * 4, cudaMemcpyDeviceToHost));
+    } else if (n_outer) {
+        memset(n_outer, 0, (size_t)s->B * 4);
+    }
+    return 0;
+}
+int to_num_constraint_rows(TOHandle s, int32_t* P) {
+    if (!s || !P) return TO_ERR_INVALID;
+    *P = s->dual_P;
+    return 0;
+}
+int to_get_duals(TOHandle s, double* lambda, double* mu, uint8_t* active) {
+    if (!s) return TO_ERR_INVALID;
+    CK_RET(s, cudaSetDevice(s->device));
+    CK_RET(s, cudaStreamSynchronize(s->stream));
+    if (s->dual_P == 0 || !s->lam_out) return 0;
+    size_t cnt = (size_t)s->B * s->dual_P;
+    if (lambda) CK_RET(s, cudaMemcpy(lambda, s->lam_out, cnt * 8, cudaMemcpyDeviceToHost));
+    if (mu) CK_RET(s, cudaMemcpy(mu, s->mu_out, cnt * 8, cudaMemcpyDeviceToHost));
+    if (active) CK_RET(s, cudaMemcpy(active, s->act_out, cnt, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- private diagnostics (csrc/debug_api.h; not part of the public header) -----------------
+// enable a first-iteration dump of problem 0: [J0, dV0, dV1, Z(all knots), K|d(all knots)]
+int to_debug_enable(TOHandle s, int32_t doubles) {
+    if (!s) return TO_ERR_INVALID;
+    CK_RET(s, cudaSetDevice(s->device));
+    if (s->debug) { cudaFree(s->debug); s->debug = nullptr; }
+    s->debug_doubles = doubles;
+    if (doubles > 0) {
+        CK_RET(s, cudaMalloc(&s->debug, (size_t)doubles * 8));
+        CK_RET(s, cudaMemset(s->debug, 0, (size_t)doubles * 8));
+    }
+    return 0;
+}
+int to_debug_read(TOHandle s, double* out, int32_t doubles) {
+    if (!s || !s->debug) return TO_ERR_INVALID;
+    CK_RET(s, cudaStreamSynchronize(s->stream));
+    CK_RET(s, cudaMemcpy(out, s->debug, (size_t)std::min<size_t>(doubles, s->debug_doubles) * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int to_debug_grid(TOHandle s, int which, int32_t* grid, int32_t* smem, uint64_t* ws_doubles) {
+    if (!s || which < 0 || which > 2 || !s->var[which].built) return TO_ERR_INVALID;
+    *grid = s->var[which].grid;
+    *smem = (int32_t)s->var[which].ki->smem_bytes;
+    *ws_doubles = s->var[which].ws_stride;
+    return 0;
+}
+
+}  // extern "C"
