@@ -225,6 +225,20 @@ int to_get_trace(TOHandle h, TOIterRecord *inner, int32_t *n_inner, TOOuterRecor
 int to_num_constraint_rows(TOHandle h, int32_t *P);
 int to_get_duals(TOHandle h, double *lambda, double *mu, uint8_t *active);
 
+/* The CUDA stream (cudaStream_t) every copy and kernel of this handle is enqueued on: lets a caller
+ * bracket the work with its own CUDA events or order other work after it. */
+int to_stream(TOHandle h, void **stream);
+/* device-to-device copy of the B result records into caller-owned device memory (e.g. the send
+ * buffer of an NCCL allgather); returns after the copy has completed. */
+int to_copy_results_device(TOHandle h, void *dst_device);
+/* Sum over the batch of the line-search trials the sequential reference semantics evaluate
+ * (index of the accepted step size + 1 per iLQR iteration; 21 on a failed search) in the last solve:
+ * the L of the roofline formulas. */
+int to_last_linesearch_trials(TOHandle h, int64_t *total);
+/* Measured register-resident FP64 FMA throughput of `device` in TFLOP/s (FMA = 2 flops): the
+ * FP64-pipe roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
+int to_measure_fp64_peak(int32_t device, double *tflops);
+
 /* library / device introspection */
 int to_device_count(void);
 const char *to_version(void);

@@ -85,7 +85,8 @@ EXPORTS = [
     "to_last_error", "to_set_batch", "to_set_batch_device", "to_set_trace", "to_solve_ilqr", "to_solve_al",
     "to_solve_altro", "to_solve_altro_async", "to_sync", "to_last_kernel_ms", "to_last_launch_count",
     "to_get_solution", "to_get_results", "to_results_device_ptr", "to_get_trace", "to_num_constraint_rows",
-    "to_get_duals", "to_device_count", "to_version",
+    "to_get_duals", "to_stream", "to_copy_results_device", "to_last_linesearch_trials", "to_measure_fp64_peak",
+    "to_device_count", "to_version",
 ]
 
 _lib = None
@@ -128,11 +129,16 @@ def load_library(path=None):
     lib.to_get_trace.argtypes = [vp, vp, vp, vp, vp]
     lib.to_num_constraint_rows.argtypes = [vp, c_int32_p]
     lib.to_get_duals.argtypes = [vp, vp, vp, vp]
+    lib.to_stream.argtypes = [vp, C.POINTER(vp)]
+    lib.to_copy_results_device.argtypes = [vp, vp]
+    lib.to_last_linesearch_trials.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.to_measure_fp64_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     lib.to_device_count.restype = C.c_int
     lib.to_version.restype = C.c_char_p
     for name in ["to_set_batch", "to_set_batch_device", "to_set_trace", "to_solve_ilqr", "to_solve_al", "to_solve_altro",
                  "to_solve_altro_async", "to_sync", "to_last_kernel_ms", "to_last_launch_count", "to_get_solution",
-                 "to_get_results", "to_results_device_ptr", "to_get_trace", "to_num_constraint_rows", "to_get_duals"]:
+                 "to_get_results", "to_results_device_ptr", "to_get_trace", "to_num_constraint_rows", "to_get_duals",
+                 "to_stream", "to_copy_results_device", "to_last_linesearch_trials", "to_measure_fp64_peak"]:
         getattr(lib, name).restype = C.c_int
     if path is None:
         _lib = lib

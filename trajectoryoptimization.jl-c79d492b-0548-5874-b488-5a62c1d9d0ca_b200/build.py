@@ -59,12 +59,13 @@ def generate():
     reg.append("    *n = d[model][0]; *m = d[model][1];\n}\n}")
     files.append(_write(os.path.join(GEN, "registry.cu"), "\n".join(reg) + "\n"))
     files.append(os.path.join(CSRC, "capi.cu"))
+    files.append(os.path.join(CSRC, "peak.cu"))
     return files
 
 
 def _deps_hash():
     h = hashlib.sha1()
-    for f in ("engine.cuh", "engine_host.h", "models.cuh", "capi.cu", "../build.py", "../../include/trajopt_b200.h"):
+    for f in ("engine.cuh", "engine_host.h", "models.cuh", "capi.cu", "peak.cu", "../build.py", "../../include/trajopt_b200.h"):
         h.update(open(os.path.join(CSRC, f), "rb").read())
     return h.hexdigest()
 

@@ -297,6 +297,7 @@ int launch(TOSolver* s, int which, int mode, const TOALOptions& alo, bool altro_
     c.write_solution = 1;
     c.o = alo;
     c.queue = s->queue;
+    c.ls_trials = (unsigned long long*)(s->queue + 2);
     c.ws = v.ws; c.ws_stride = v.ws_stride;
     c.debug_flag = nullptr;
     c.debug = nullptr;
@@ -328,6 +329,7 @@ int solve_common(TOSolver* s, int api_mode, const TOALTROOptions& ao, bool sync)
     s->launches = 0;
     const bool con = constrained(s);
     const double* X0_in = s->has_X0 ? s->X0 : nullptr;
+    CK_RET(s, cudaMemsetAsync(s->queue, 0, 256, s->stream));
     CK_RET(s, cudaEventRecord(s->ev0, s->stream));
     if (api_mode == 0) {
         if ((rc = build_variant(s, 0, &ao))) return rc;
@@ -596,6 +598,32 @@ int to_get_duals(TOHandle s, double* lambda, double* mu, uint8_t* active) {
     if (mu) CK_RET(s, cudaMemcpy(mu, s->mu_out, cnt * 8, cudaMemcpyDeviceToHost));
     if (active) CK_RET(s, cudaMemcpy(active, s->act_out, cnt, cudaMemcpyDeviceToHost));
     return 0;
+}
+
+int to_stream(TOHandle s, void** stream) {
+    if (!s || !stream) return TO_ERR_INVALID;
+    *stream = (void*)s->stream;
+    return 0;
+}
+int to_copy_results_device(TOHandle s, void* dst) {
+    if (!s || !dst) return TO_ERR_INVALID;
+    CK_RET(s, cudaSetDevice(s->device));
+    CK_RET(s, cudaMemcpyAsync(dst, s->res, (size_t)s->B * sizeof(TOResult), cudaMemcpyDeviceToDevice, s->stream));
+    CK_RET(s, cudaStreamSynchronize(s->stream));
+    return 0;
+}
+int to_last_linesearch_trials(TOHandle s, int64_t* total) {
+    if (!s || !total) return TO_ERR_INVALID;
+    CK_RET(s, cudaSetDevice(s->device));
+    CK_RET(s, cudaStreamSynchronize(s->stream));
+    unsigned long long v = 0;
+    CK_RET(s, cudaMemcpy(&v, s->queue + 2, 8, cudaMemcpyDeviceToHost));
+    *total = (int64_t)v;
+    return 0;
+}
+int to_measure_fp64_peak(int32_t device, double* tflops) {
+    if (!tflops) return TO_ERR_INVALID;
+    return tob::measure_fp64_peak(device, tflops);
 }
 
 // ---- private diagnostics (csrc/debug_api.h; not part of the public header) -----------------

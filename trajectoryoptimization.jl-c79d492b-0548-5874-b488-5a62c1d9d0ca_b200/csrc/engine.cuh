@@ -255,6 +255,7 @@ struct Solver {
     double fp_expected, fp_z, fp_alpha;
     int outer_idx;
     int n_inner_rec, n_outer_rec;
+    unsigned long long ls_count;
     double x0[C::n];
 
     __device__ Solver(const DevProblem& P_, const DevBatch& B_, const DevCtl& c_, Smem<C>& s_, double* ws_, int lane_)
@@ -1013,6 +1014,7 @@ struct Solver {
         double Jres;
         if (msk != 0) {
             const int w = __ffs(msk) - 1;
+            ls_count += (unsigned long long)(w + 1);
             Jres = bcast(Jt, w);
             fp_expected = bcast(expected, w);
             fp_z = bcast(z, w);
@@ -1027,6 +1029,7 @@ struct Solver {
             }
         } else {
             // line search failed (forward_pass.jl:22-37): X̄ ← X, Ū ← U, J recomputed, regularisation bumped
+            ls_count += (unsigned long long)ntrial;
             Jres = eval_cost();
             fp_expected = 0.0;
             fp_z = 0.0;
@@ -1252,7 +1255,7 @@ struct Solver {
         b = b_;
         const int N = P.N;
         io = ctl.o.opts_uncon;
-        status = 0; steps = 0; n_inner_rec = 0; n_outer_rec = 0;
+        status = 0; steps = 0; n_inner_rec = 0; n_outer_rec = 0; ls_count = 0;
         last_cost = 0.0; last_dJ = 0.0; last_grad = 0.0;
         if (ctl.accumulate) {
             status = Bt.res[b].status;
@@ -1326,6 +1329,7 @@ struct Solver {
             Bt.res[b] = r;
             if (Bt.inner_cap > 0) Bt.n_inner[b] = n_inner_rec;
             if (Bt.outer_cap > 0) Bt.n_outer[b] = n_outer_rec;
+            if (ctl.ls_trials) atomicAdd(ctl.ls_trials, ls_count);
         }
         if (ctl.write_solution) {
             const int no = Bt.n_out, mo = Bt.m_out;
