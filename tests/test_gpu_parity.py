@@ -1,0 +1,167 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA engine, called through the C ABI,
+against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): iteration counts, status and active-set masks BIT-EXACT; per-iteration
+cost J, final X/U and constraint violation within 1e-8 relative.  The engine and the oracle share one
+arithmetic contract (sequential FMA chains for inner products, no other contraction, a common
+sin/cos), so in practice every float below is bit-identical too — the tests assert the stated
+tolerance and additionally report exact equality for the integer observables.
+"""
+import numpy as np
+import pytest
+
+from cases import CASES
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-8  # north_star tolerance for floating-point observables
+
+
+def _solve_gpu(to, prob, opts, x0, X0, B, inner_cap=2048, outer_cap=96):
+    bs = to.api.BatchSolver(prob, B, 0, inner_cap, outer_cap)
+    try:
+        bs.set_batch(x0, np.broadcast_to(prob.U, (B,) + prob.U.shape), X0)
+        bs.solve(opts)
+        X, U, dts = bs.solution()
+        inner, outer = bs.trace()
+        lam, mu, act = bs.duals()
+        return dict(results=bs.results(), X=X, U=U, dts=dts, inner=inner, outer=outer, lam=lam, mu=mu, act=act,
+                    ms=bs.kernel_ms(), launches=bs.launches())
+    finally:
+        bs.close()
+
+
+def _close(a, b, rtol=RTOL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    both_nan = np.isnan(a) & np.isnan(b)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    ok = both_nan | both_inf | (np.abs(a - b) <= rtol * np.maximum(np.abs(a), np.abs(b)) + 1e-300)
+    return bool(np.all(ok))
+
+
+def _compare(ref, gpu, B, atol_xu=1e-10):
+    for f in ("iterations_total", "iterations_outer", "status", "steps"):
+        assert np.array_equal(ref["results"][f], gpu["results"][f]), (f, ref["results"][f], gpu["results"][f])
+    assert _close(ref["results"]["J"], gpu["results"]["J"]) and _close(ref["results"]["c_max"], gpu["results"]["c_max"])
+    fin = np.isfinite(ref["X"]).all(axis=(1, 2))
+    assert np.allclose(ref["X"][fin], gpu["X"][fin], rtol=RTOL, atol=atol_xu)
+    assert np.allclose(ref["U"][fin], gpu["U"][fin], rtol=RTOL, atol=atol_xu)
+    assert np.allclose(ref["dts"][fin], gpu["dts"][fin], rtol=RTOL, atol=0)
+    for b in range(B):
+        ri, gi = ref["inner"][b], gpu["inner"][b]
+        assert len(ri) == len(gi)
+        for f in ("iter", "outer"):
+            assert np.array_equal(ri[f], gi[f])
+        assert np.array_equal(ri["alpha"], gi["alpha"])          # accepted step sizes: bit-exact
+        assert np.array_equal(ri["rho"] > 0, gi["rho"] > 0)
+        for f in ("cost", "dJ", "gradient", "expected", "z", "rho"):
+            assert _close(ri[f], gi[f], 1e-8 if f in ("cost", "rho") else 1e-6), (b, f)
+        ro, go = ref["outer"][b], gpu["outer"][b]
+        assert len(ro) == len(go) and np.array_equal(ro["iterations_inner"], go["iterations_inner"])
+        assert _close(ro["cost"], go["cost"]) and _close(ro["c_max"], go["c_max"]) and _close(ro["penalty_max"], go["penalty_max"])
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if c not in ("escape_altro",)])
+def test_parity_small_batches(to, oracle, name):
+    B = 8
+    prob, opts, x0, X0 = CASES[name](B)
+    ref = oracle.solve(prob, opts, x0=x0, X0=X0, B=B, inner_cap=2048, outer_cap=96)
+    gpu = _solve_gpu(to, prob, opts, x0, X0, B)
+    _compare(ref, gpu, B)
+
+
+def test_parity_car_escape_170_circles(to, oracle):
+    B = 2  # 177 constraint rows per knot: slow on one warp, keep it small
+    prob, opts, x0, X0 = CASES["escape_altro"](B)
+    ref = oracle.solve(prob, opts, x0=x0, X0=X0, B=B, inner_cap=2048, outer_cap=96)
+    gpu = _solve_gpu(to, prob, opts, x0, X0, B)
+    _compare(ref, gpu, B)
+
+
+def test_duals_and_active_set_bit_exact(to, oracle):
+    """active-set masks bit-exact; λ, μ to 1e-8 (quadrotor ALTRO and the README block move)."""
+    for name, B in (("quad_altro", 4), ("di_altro", 1), ("cart_altro", 4)):
+        prob, opts, x0, X0 = CASES[name](B)
+        ref = oracle.solve(prob, opts, x0=x0, X0=X0, B=B, inner_cap=0, outer_cap=0, want_duals=True)
+        gpu = _solve_gpu(to, prob, opts, x0, X0, B)
+        assert ref["act"].shape == gpu["act"].shape and np.array_equal(ref["act"], gpu["act"])
+        assert _close(ref["lam"], gpu["lam"]) and _close(ref["mu"], gpu["mu"])
+
+
+def test_readme_block_move(to):
+    """README.md:29-67 through the reference-style API: solve!(prob, ALTROSolverOptions{Float64}())."""
+    prob = to.problems.doubleintegrator()
+    solver = to.solve_b(prob, to.ALTROSolverOptions())
+    assert solver.status == 0 and to.max_violation(prob) < 1e-3
+    assert np.all(np.abs(prob.U) <= 1.5 + 1e-3) and np.linalg.norm(prob.X[-1] - prob.xf) < 1e-3
+    assert solver.stats["iterations"] == len(solver.stats["cost"]) == len(solver.stats["c_max"])
+
+
+def test_reference_integration_inequalities(to):
+    """The reference's own solve-level tests, re-expressed as batch-of-1 solves:
+    test/quadrotor_tests.jl:39-60 (iLQR reaches xf; AL with control bounds max_violation < tol),
+    test/car_tests.jl:31-32 (parallel park), test/minimum_time_tests.jl:38-46 (total time shrinks)."""
+    p = to.problems.quadrotor()
+    p.constraints = to.Constraints(p.N)
+    to.solve_b(p, to.iLQRSolverOptions())
+    assert np.linalg.norm(p.X[-1] - p.xf) < 5e-3
+    p = to.problems.quadrotor()
+    s = to.solve_b(p, to.problems.quadrotor_bench_options())
+    assert to.max_violation(p) < 1e-3 and s.c_max < 1e-3
+    p = to.problems.parallel_park()
+    p.constraints = to.Constraints(p.N)
+    to.solve_b(p, to.iLQRSolverOptions())
+    assert np.linalg.norm(p.X[-1] - p.xf) < 1e-3
+    p = to.problems.pendulum()
+    tt = p.dt * (p.N - 1)
+    p.tf = 0.0
+    al = to.AugmentedLagrangianSolverOptions(iterations=50, penalty_scaling=10.0)
+    to.solve_b(p, to.ALTROSolverOptions(opts_al=al, R_minimum_time=15.0, dt_max=0.15, dt_min=1e-3))
+    assert to.total_time(p) < 0.5 * tt and to.max_violation(p) < 1e-3
+
+
+def test_batched_solve_matches_singles_and_is_order_independent(to):
+    """The new batched solve!: B problems at once == B single solves (queue order must not matter)."""
+    B = 64
+    prob, opts, x0, _ = CASES["cart_altro"](B)
+    big = _solve_gpu(to, prob, opts, x0, None, B, inner_cap=0, outer_cap=0)
+    perm = np.random.default_rng(0).permutation(B)
+    shuf = _solve_gpu(to, prob, opts, x0[perm], None, B, inner_cap=0, outer_cap=0)
+    assert big["results"][perm].tobytes() == shuf["results"].tobytes()
+    assert np.array_equal(big["X"][perm], shuf["X"]) and np.array_equal(big["U"][perm], shuf["U"])
+    one = _solve_gpu(to, prob, opts, x0[5:6], None, 1, inner_cap=0, outer_cap=0)
+    assert one["results"].tobytes() == big["results"][5:6].tobytes() and np.array_equal(one["X"][0], big["X"][5])
+
+
+def test_full_size_properties_quadrotor(to, oracle):
+    """A larger batch (size-independent properties): every problem converges with c_max < tol, the
+    returned trajectories are dynamically feasible under the oracle's rk3 (X[k+1] == fd(X[k],U[k])
+    bit for bit), controls respect u >= -tol, and a sampled subset matches the oracle exactly."""
+    B = 2048
+    prob, opts, x0, _ = CASES["quad_altro"](B)
+    gpu = _solve_gpu(to, prob, opts, x0, None, B, inner_cap=0, outer_cap=0)
+    r = gpu["results"]
+    assert np.all(r["status"] == 0) and np.all(r["c_max"] < 1e-3) and np.all(r["steps"] == r["iterations_total"] - r["iterations_outer"] + 1)
+    assert gpu["U"].min() > -1e-3
+    for b in (0, 777, 2047):
+        for k in (0, 50, 99):
+            xn = oracle.discrete(4, 0, gpu["X"][b, k], gpu["U"][b, k], prob.dt)
+            assert np.array_equal(xn, gpu["X"][b, k + 1])
+    idx = np.array([0, 1, 1023, 2047])
+    ref = oracle.solve(prob, opts, x0=x0[idx], B=len(idx), inner_cap=0, outer_cap=0)
+    assert ref["results"].tobytes() == r[idx].tobytes() and np.array_equal(ref["X"], gpu["X"][idx])
+
+
+def test_errors_are_reported_not_thrown(to):
+    import ctypes as C
+    prob = to.problems.doubleintegrator()
+    bs = to.api.BatchSolver(prob, 1, 0)
+    try:
+        with pytest.raises(RuntimeError, match="to_set_batch"):
+            bs.solve(to.ALTROSolverOptions())
+        bs.set_batch(prob.x0[None], prob.U[None])
+        o = to.ALTROSolverOptions()
+        o.opts_al.opts_uncon.iterations_linesearch = 40
+        with pytest.raises(RuntimeError, match="iterations_linesearch"):
+            bs.solve(o)
+    finally:
+        bs.close()

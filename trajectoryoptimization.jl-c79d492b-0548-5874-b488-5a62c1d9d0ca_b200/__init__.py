@@ -4,5 +4,5 @@ Only what the hot path needs lives here: `csrc/` (CUDA kernels + the C ABI of in
 `abi.py` (ctypes mirror of that header), `api.py` (host mirror of the reference's user API) and
 `problems.py` (the reference's problem zoo as data).
 """
-from . import abi, api, problems  # noqa: F401
+from . import abi, api, problems, sharding  # noqa: F401
 from .api import *  # noqa: F401,F403
