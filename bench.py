@@ -92,6 +92,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+T0 = time.time()
+
+
+def log(msg):
+    """progress on stderr (stdout carries only the JSON line)"""
+    sys.stderr.write("[bench %7.1fs] %s\n" % (time.time() - T0, msg))
+    sys.stderr.flush()
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -227,9 +236,11 @@ def main():
         e1.synchronize()
         return e0.elapsed_time(e1)
 
+    log("inputs ready (B=%d per GPU), engine=%s" % (B, os.environ.get("TRAJOPT_B200_ENGINE", "lockstep")))
     check(lib.to_set_batch(bs.h, x0_h.data_ptr(), U0_h.data_ptr(), None))
-    for _ in range(args.warmup):
-        resident_step()
+    for i in range(args.warmup):
+        ms = resident_step()
+        log("warmup %d: %.1f ms, %d launches" % (i, ms, bs.launches()))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -240,6 +251,7 @@ def main():
         ms = resident_step()
         step_ms.append(ms)
         kernel_ms.append(bs.kernel_ms())
+        log("timed step: %.1f ms" % ms)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = bs.launches() * args.steps
@@ -247,6 +259,7 @@ def main():
     trials = C.c_int64()
     check(lib.to_last_linesearch_trials(bs.h, C.byref(trials)))
     e2e_ms = [e2e_step() for _ in range(max(1, min(2, args.steps)))]
+    log("e2e steps: %s ms" % e2e_ms)
     clocks = sampler.stop() if rank == 0 else None
     barrier()
 
@@ -325,6 +338,7 @@ def main():
             import oracle_py
             cores = host_cores()
             sample = args.cpu_sample or 6 * cores
+            log("cpu baseline: %d problems on %d threads" % (sample, cores))
             t0 = time.perf_counter()
             r = oracle_py.solve(prob, opts, x0=x0_np[:sample], B=sample, inner_cap=0, outer_cap=0, threads=cores)
             dt = time.perf_counter() - t0

@@ -44,3 +44,27 @@ def printed_close(value, printed, extra_rel=0.0):
     expo = int(s.split("e")[1]) if "e" in s else 0
     ulp = 10.0 ** (expo - decimals)
     return abs(value - ref) <= 1.01 * ulp + extra_rel * abs(ref)
+
+
+def quadrotor_test_problem(to, kind):
+    """test/quadrotor_tests.jl:1-60: rk4 quadrotor, Q=R=1e-2 I, Qf=1000 I, fly 50 m in y, N=101, dt=0.05,
+    hover controls; `kind` in {"none", "goal", "goal+bounds"}."""
+    import numpy as np
+    n, m, N, dt = 13, 4, 101, 0.05
+    x0 = np.zeros(n)
+    x0[3] = 1.0
+    xf = x0.copy()
+    xf[1] = 50.0
+    obj = to.LQRObjective(1e-2 * np.eye(n), 1e-2 * np.eye(m), 1000.0 * np.eye(n), xf, N)
+    cons = to.Constraints(N)
+    if "bounds" in kind:
+        for k in range(N - 1):
+            cons.add(k, to.BoundConstraint(n, m, u_min=0.0, u_max=15.0))
+    if "goal" in kind:
+        cons.add(N - 1, to.goal_constraint(xf))
+    p = to.Problem(to.rk4(to.Dynamics.quadrotor), obj, constraints=cons, x0=x0, xf=xf, N=N, dt=dt,
+                   U0=np.full((N - 1, m), 0.5 * 9.81 / 4.0))
+    il = to.iLQRSolverOptions(cost_tolerance=1e-5)
+    al = to.AugmentedLagrangianSolverOptions(opts_uncon=il, constraint_tolerance=1e-3, cost_tolerance=1e-5,
+                                             cost_tolerance_intermediate=1e-4)
+    return p, il, al

@@ -98,12 +98,18 @@ def test_readme_block_move(to):
 
 def test_reference_integration_inequalities(to):
     """The reference's own solve-level tests, re-expressed as batch-of-1 solves:
-    test/quadrotor_tests.jl:39-60 (iLQR reaches xf; AL with control bounds max_violation < tol),
+    test/quadrotor_tests.jl:1-60 (rk4; iLQR reaches xf; AL with goal; AL with goal + control bounds),
     test/car_tests.jl:31-32 (parallel park), test/minimum_time_tests.jl:38-46 (total time shrinks)."""
-    p = to.problems.quadrotor()
-    p.constraints = to.Constraints(p.N)
-    to.solve_b(p, to.iLQRSolverOptions())
+    from helpers import quadrotor_test_problem
+    p, il, al = quadrotor_test_problem(to, "none")
+    to.solve_b(p, il)
     assert np.linalg.norm(p.X[-1] - p.xf) < 5e-3
+    p, il, al = quadrotor_test_problem(to, "goal")
+    to.solve_b(p, al)
+    assert np.abs(p.X[-1] - p.xf).max() < al.constraint_tolerance and to.max_violation(p) < al.constraint_tolerance
+    p, il, al = quadrotor_test_problem(to, "goal+bounds")
+    to.solve_b(p, al)
+    assert np.linalg.norm(p.X[-1] - p.xf) < al.constraint_tolerance and to.max_violation(p) < al.constraint_tolerance
     p = to.problems.quadrotor()
     s = to.solve_b(p, to.problems.quadrotor_bench_options())
     assert to.max_violation(p) < 1e-3 and s.c_max < 1e-3

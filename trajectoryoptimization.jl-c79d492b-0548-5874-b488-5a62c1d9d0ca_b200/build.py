@@ -45,7 +45,7 @@ def generate():
     files = []
     for inst in INSTANCES:
         mo, ig, inf, mt, pc = inst
-        src = ('#include "../engine.cuh"\nnamespace tob {\nKernelInfo tob_info_%s() { return make_info<Cfg<%d, %d, %s, %s, %d>>(); }\n}\n'
+        src = ('#include "../lockstep.cuh"\nnamespace tob {\nKernelInfo tob_info_%s() { return make_info<Cfg<%d, %d, %s, %s, %d>>(); }\n}\n'
                % (_name(inst), mo, ig, "true" if inf else "false", "true" if mt else "false", pc))
         files.append(_write(os.path.join(GEN, "inst_%s.cu" % _name(inst)), src))
     reg = ['#include <vector>\n#include "../engine_host.h"\nnamespace tob {']
@@ -65,7 +65,7 @@ def generate():
 
 def _deps_hash():
     h = hashlib.sha1()
-    for f in ("engine.cuh", "engine_host.h", "models.cuh", "capi.cu", "peak.cu", "../build.py", "../../include/trajopt_b200.h"):
+    for f in ("engine.cuh", "lockstep.cuh", "engine_host.h", "models.cuh", "capi.cu", "peak.cu", "../build.py", "../../include/trajopt_b200.h"):
         h.update(open(os.path.join(CSRC, f), "rb").read())
     return h.hexdigest()
 

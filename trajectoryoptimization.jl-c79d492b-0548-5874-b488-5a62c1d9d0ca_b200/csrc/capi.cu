@@ -4,6 +4,7 @@
 // nothing here computes on the CPU and there is no fallback path.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -42,6 +43,11 @@ struct Variant {
     unsigned long long ws_stride = 0;
     double* ws = nullptr;
     double key[6] = {0, 0, 0, 0, 0, 0};  // ALTRO parameters the variant was built with
+    // lockstep engine buffers
+    bool ls_ready = false;
+    LsCtl lc{};
+    LsGrids grids{};
+    int* ls_lists = nullptr;
 };
 
 }  // namespace
@@ -74,6 +80,10 @@ struct TOSolver {
     int launches = 0;
     int sm_count = 0;
     int blocks_per_sm_override = 0;
+    int engine = 1;              // 0 = warp-persistent kernel (engine.cuh), 1 = lockstep phase kernels (lockstep.cuh)
+    int ticks = 0;               // lockstep ticks enqueued by the last solve
+    unsigned int* h_counts = nullptr;  // pinned ring of active-list sizes read back from the device
+    cudaEvent_t ring_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
 
     int fail(int code, const std::string& msg) {
@@ -117,6 +127,13 @@ void free_variant(Variant& v) {
     v.allocs.clear();
     if (v.ws) cudaFree(v.ws);
     v.ws = nullptr;
+    if (v.lc.ws) cudaFree(v.lc.ws);
+    if (v.lc.st) cudaFree(v.lc.st);
+    if (v.lc.counts) cudaFree(v.lc.counts);
+    if (v.ls_lists) cudaFree(v.ls_lists);
+    v.lc = LsCtl{};
+    v.ls_lists = nullptr;
+    v.ls_ready = false;
     v.built = false;
 }
 
@@ -236,20 +253,96 @@ int build_variant(TOSolver* s, int which, const TOALTROOptions* ao) {
     if ((rc = upload(s, v, kb, &P.knot_row_begin))) return rc;
     if ((rc = upload(s, v, kc, &P.knot_row_count))) return rc;
     if ((rc = upload(s, v, lo, &P.knot_lam_off))) return rc;
-    // grid + workspace
-    int per_sm = s->blocks_per_sm_override > 0 ? s->blocks_per_sm_override : v.ki->max_blocks_per_sm();
-    if (per_sm < 1) return s->fail(TO_ERR_CUDA, "kernel cannot be resident (occupancy 0)");
-    long long grid = (long long)s->sm_count * per_sm;
-    if (grid > s->B) grid = s->B;
-    v.grid = (int)grid;
-    v.ws_stride = v.ki->ws_doubles(N, P.Ptot);
-    size_t bytes = (size_t)v.grid * v.ws_stride * sizeof(double);
-    if (cudaMalloc(&v.ws, bytes) != cudaSuccess) {
-        char buf[128];
-        snprintf(buf, sizeof buf, "cudaMalloc of %.1f MB workspace failed", bytes / 1048576.0);
+    v.built = true;
+    return 0;
+}
+
+// workspace of the selected engine (allocated on first use)
+int ensure_engine_buffers(TOSolver* s, Variant& v) {
+    const int N = s->d.N;
+    char buf[160];
+    if (s->engine == 0) {
+        if (v.ws) return 0;
+        int per_sm = s->blocks_per_sm_override > 0 ? s->blocks_per_sm_override : v.ki->max_blocks_per_sm();
+        if (per_sm < 1) return s->fail(TO_ERR_CUDA, "kernel cannot be resident (occupancy 0)");
+        long long grid = (long long)s->sm_count * per_sm;
+        if (grid > s->B) grid = s->B;
+        v.grid = (int)grid;
+        v.ws_stride = v.ki->ws_doubles(N, v.P.Ptot);
+        size_t bytes = (size_t)v.grid * v.ws_stride * sizeof(double);
+        if (cudaMalloc(&v.ws, bytes) != cudaSuccess) {
+            snprintf(buf, sizeof buf, "cudaMalloc of %.1f MB workspace failed", bytes / 1048576.0);
+            return s->fail(TO_ERR_NOMEM, buf);
+        }
+        return 0;
+    }
+    if (v.ls_ready) return 0;
+    const size_t B = (size_t)s->B;
+    v.lc.ws_stride = v.ki->ls_ws_doubles(N, v.P.Ptot);
+    const size_t bytes = B * v.lc.ws_stride * sizeof(double);
+    if (cudaMalloc(&v.lc.ws, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        snprintf(buf, sizeof buf, "cudaMalloc of %.1f MB per-problem workspaces failed", bytes / 1048576.0);
         return s->fail(TO_ERR_NOMEM, buf);
     }
-    v.built = true;
+    if (cudaMalloc(&v.lc.st, B * sizeof(LsState)) != cudaSuccess || cudaMalloc(&v.ls_lists, 5 * B * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&v.lc.counts, 64) != cudaSuccess)
+        return s->fail(TO_ERR_NOMEM, "cudaMalloc failed (lockstep state)");
+    v.lc.list[0] = v.ls_lists; v.lc.list[1] = v.ls_lists + B;
+    v.lc.retry[0] = v.ls_lists + 2 * B; v.lc.retry[1] = v.ls_lists + 3 * B;
+    v.lc.outer_list = v.ls_lists + 4 * B;
+    int rc = v.ki->ls_setup(s->sm_count, &v.grids);
+    if (rc != 0) {
+        snprintf(buf, sizeof buf, "lockstep kernel setup failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+        return s->fail(TO_ERR_CUDA, buf);
+    }
+    if (s->blocks_per_sm_override > 0) {
+        v.grids.jac = s->sm_count * s->blocks_per_sm_override;
+        v.grids.bp = s->sm_count * std::min(s->blocks_per_sm_override, std::max(1, v.grids.occ_bp));
+        v.grids.trial = s->sm_count * s->blocks_per_sm_override;
+    }
+    v.ls_ready = true;
+    return 0;
+}
+
+// the lockstep engine: init kernel, then replay the tick (jac, bp, trial groups, accept, outer)
+// until the active list is empty.  The host learns the list size from an asynchronous read-back
+// that trails the enqueued work by LAG ticks, so the stream never drains between ticks.
+int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
+    const int LAG = 4, RING = 8;
+    cudaStream_t st = s->stream;
+    CK_RET(s, cudaMemsetAsync(v.lc.counts, 0, 64, st));
+    CK_RET(s, cudaMemsetAsync(v.lc.st, 0, (size_t)s->B * sizeof(LsState), st));
+    v.ki->ls_launch(LS_PHASE_INIT, v.grids, st, v.P, Bt, c, v.lc, 0, 0);
+    CK_RET(s, cudaGetLastError());
+    s->launches += 1;
+    const int ntrial = c.o.opts_uncon.iterations_linesearch + 1;
+    const int G = v.grids.trial_group;
+    const int ngroups = (ntrial + G - 1) / G;
+    // worst case number of ticks: every AL iteration runs every allowed inner step
+    const long long max_ticks = (long long)std::max(1, c.o.iterations) * (long long)std::max(1, c.o.opts_uncon.iterations) + 8;
+    for (long long t = 0; t < max_ticks; t++) {
+        const int cur = (int)(t & 1);
+        v.ki->ls_launch(LS_PHASE_JAC, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+        v.ki->ls_launch(LS_PHASE_BP, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+        for (int g = 0; g < ngroups; g++) {
+            if (g >= 2) CK_RET(s, cudaMemsetAsync(v.lc.counts + 2 + (g & 1), 0, sizeof(unsigned int), st));
+            v.ki->ls_launch(LS_PHASE_TRIAL, v.grids, st, v.P, Bt, c, v.lc, cur, g);
+        }
+        v.ki->ls_launch(LS_PHASE_ACCEPT, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+        v.ki->ls_launch(LS_PHASE_OUTER, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+        CK_RET(s, cudaGetLastError());
+        s->launches += 4 + ngroups;
+        s->ticks += 1;
+        const int slot = (int)(t % RING);
+        CK_RET(s, cudaMemcpyAsync(&s->h_counts[slot], v.lc.counts + (cur ^ 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CK_RET(s, cudaEventRecord(s->ring_ev[slot], st));
+        if (t >= LAG) {
+            const int old = (int)((t - LAG) % RING);
+            CK_RET(s, cudaEventSynchronize(s->ring_ev[old]));
+            if (s->h_counts[old] == 0) return 0;
+        }
+    }
     return 0;
 }
 
@@ -305,6 +398,10 @@ int launch(TOSolver* s, int which, int mode, const TOALOptions& alo, bool altro_
         size_t need = v.ki->debug_doubles(s->d.N);
         if (need <= s->debug_doubles) c.debug = s->debug;
     }
+    rc = ensure_engine_buffers(s, v);
+    if (rc) return rc;
+    c.ws = v.ws; c.ws_stride = v.ws_stride;
+    if (s->engine == 1) return run_lockstep(s, v, Bt, c);
     CK_RET(s, cudaMemsetAsync(s->queue, 0, sizeof(unsigned int), s->stream));
     v.ki->launch(v.grid, s->stream, v.P, Bt, c);
     CK_RET(s, cudaGetLastError());
@@ -327,6 +424,7 @@ int solve_common(TOSolver* s, int api_mode, const TOALTROOptions& ao, bool sync)
     if (rc) return rc;
     const TOALOptions& alo = ao.opts_al;
     s->launches = 0;
+    s->ticks = 0;
     const bool con = constrained(s);
     const double* X0_in = s->has_X0 ? s->X0 : nullptr;
     CK_RET(s, cudaMemsetAsync(s->queue, 0, 256, s->stream));
@@ -430,6 +528,8 @@ int to_create(const TOProblemDesc* desc, int32_t B, int32_t device, TOHandle* ou
     s->sm_count = prop.multiProcessorCount;
     const char* env = getenv("TRAJOPT_B200_BLOCKS_PER_SM");
     if (env) s->blocks_per_sm_override = atoi(env);
+    env = getenv("TRAJOPT_B200_ENGINE");  // "persistent" selects the single-kernel engine (cross-check / tiny batches)
+    if (env && (env[0] == 'p' || env[0] == '0')) s->engine = 0;
     bool ok = true;
     ok &= cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok &= cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess;
@@ -440,6 +540,8 @@ int to_create(const TOProblemDesc* desc, int32_t B, int32_t device, TOHandle* ou
     ok &= cudaMalloc(&s->dts, (size_t)B * (N - 1) * 8) == cudaSuccess;
     ok &= cudaMalloc(&s->res, (size_t)B * sizeof(TOResult)) == cudaSuccess;
     ok &= cudaMalloc(&s->queue, 256) == cudaSuccess;
+    ok &= cudaMallocHost(&s->h_counts, 8 * sizeof(unsigned int)) == cudaSuccess;
+    for (auto& e : s->ring_ev) ok &= cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { to_destroy(s); return fail_create(TO_ERR_NOMEM, "device allocation failed in to_create"); }
     cudaMemset(s->res, 0, (size_t)B * sizeof(TOResult));
     *out = s;
@@ -454,6 +556,8 @@ void to_destroy(TOHandle s) {
     void* ptrs[] = {s->x0, s->U0, s->X0, s->X, s->U, s->dts, s->res, s->inner, s->outer, s->n_inner, s->n_outer,
                     s->lam_out, s->mu_out, s->act_out, s->queue, s->debug};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (s->h_counts) cudaFreeHost(s->h_counts);
+    for (auto& e : s->ring_ev) if (e) cudaEventDestroy(e);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -647,9 +751,26 @@ int to_debug_read(TOHandle s, double* out, int32_t doubles) {
 }
 int to_debug_grid(TOHandle s, int which, int32_t* grid, int32_t* smem, uint64_t* ws_doubles) {
     if (!s || which < 0 || which > 2 || !s->var[which].built) return TO_ERR_INVALID;
+    if (s->engine == 1) {
+        *grid = s->var[which].grids.bp;
+        *smem = s->var[which].grids.bp_smem;
+        *ws_doubles = s->var[which].lc.ws_stride;
+        return 0;
+    }
     *grid = s->var[which].grid;
     *smem = (int32_t)s->var[which].ki->smem_bytes;
     *ws_doubles = s->var[which].ws_stride;
+    return 0;
+}
+// engine selection (0 = warp-persistent single kernel, 1 = lockstep phase kernels) and tick count of the last solve
+int to_debug_set_engine(TOHandle s, int32_t engine) {
+    if (!s || engine < 0 || engine > 1) return TO_ERR_INVALID;
+    s->engine = engine;
+    return 0;
+}
+int to_debug_ticks(TOHandle s, int32_t* ticks) {
+    if (!s || !ticks) return TO_ERR_INVALID;
+    *ticks = s->ticks;
     return 0;
 }
 

@@ -39,7 +39,7 @@ struct WsLayout {
     unsigned long long X, U, Z, KD, LAM, MU, XB, UB, QST, CB, total;
 };
 template <class C>
-__host__ __device__ inline WsLayout ws_layout(int N, int Ptot) {
+__host__ __device__ inline WsLayout ws_layout(int N, int Ptot, bool candidates = true) {
     WsLayout L;
     unsigned long long o = 0;
     L.X = o;   o += (unsigned long long)N * C::n;
@@ -48,8 +48,9 @@ __host__ __device__ inline WsLayout ws_layout(int N, int Ptot) {
     L.KD = o;  o += (unsigned long long)(N - 1) * C::KDS;
     L.LAM = o; o += Ptot;
     L.MU = o;  o += Ptot;
-    L.XB = o;  o += (unsigned long long)N * C::n * 32;
-    L.UB = o;  o += (unsigned long long)(N - 1) * C::m * 32;
+    // 32 candidate trajectories of the parallel line search (persistent engine only)
+    L.XB = o;  o += candidates ? (unsigned long long)N * C::n * 32 : 0ull;
+    L.UB = o;  o += candidates ? (unsigned long long)(N - 1) * C::m * 32 : 0ull;
     L.QST = o; o += (unsigned long long)(N - 1) * C::QS;
     L.CB = o;  o += 2ull * N;
     L.total = (o + 15ull) & ~15ull;
@@ -258,8 +259,8 @@ struct Solver {
     unsigned long long ls_count;
     double x0[C::n];
 
-    __device__ Solver(const DevProblem& P_, const DevBatch& B_, const DevCtl& c_, Smem<C>& s_, double* ws_, int lane_)
-        : P(P_), Bt(B_), ctl(c_), sm(s_), ws(ws_), L(ws_layout<C>(P_.N, P_.Ptot)), lane(lane_) {}
+    __device__ Solver(const DevProblem& P_, const DevBatch& B_, const DevCtl& c_, Smem<C>& s_, double* ws_, int lane_, bool candidates = true)
+        : P(P_), Bt(B_), ctl(c_), sm(s_), ws(ws_), L(ws_layout<C>(P_.N, P_.Ptot, candidates)), lane(lane_) {}
 
     __device__ double* X(int k) { return ws + L.X + (size_t)k * C::n; }
     __device__ double* U(int k) { return ws + L.U + (size_t)k * C::m; }
@@ -1249,8 +1250,8 @@ struct Solver {
         return true;
     }
 
-    // ---- load one problem into the workspace, solve, write results ----
-    __device__ void run(int b_) {
+    // ---- load one problem into the workspace (altro_methods.jl:98-124 initialisation included) ----
+    __device__ void prologue(int b_) {
         constexpr int n = C::n, m = C::m, n0 = C::n0, m0 = C::m0;
         b = b_;
         const int N = P.N;
@@ -1265,8 +1266,7 @@ struct Solver {
         }
         const double nanv = __longlong_as_double(0x7ff8000000000000LL);
         // x0, X, U
-#pragma unroll
-        for (int i = 0; i < n; i++) x0[i] = (i < n0) ? Bt.x0[(size_t)b * n0 + i] : 0.0;
+        load_x0();
         const double sdt = sqrt(P.dt);
         for (int e = lane; e < N * n; e += 32) {
             const int k = e / n, i = e - k * n;
@@ -1304,24 +1304,16 @@ struct Solver {
             __syncwarp();
         }
         if (ctl.projection_first) rollout_open(true);
-        // solve
-        al_on = false;
-        double Jout = 0.0, cmax = 0.0;
-        int al_it = 0, al_tot = 0;
-        bool ok;
-        if (ctl.mode == 0) {
-            const size_t nk = (size_t)(N - 1) * C::KDS;
-            for (size_t e = lane; e < nk; e += 32) ws[L.KD + e] = 0.0;
-            __syncwarp();
-            outer_idx = 0;
-            ok = ilqr_solve();
-            Jout = last_cost;
-            al_tot = iterations;
-        } else {
-            ok = al_solve(Jout, cmax, al_it, al_tot);
-        }
-        (void)ok;
-        // results
+    }
+    __device__ void load_x0() {
+#pragma unroll
+        for (int i = 0; i < C::n; i++) x0[i] = (i < C::n0) ? Bt.x0[(size_t)b * C::n0 + i] : 0.0;
+    }
+
+    // ---- write the result record, the solution and (AL) the multipliers / active set ----
+    __device__ void epilogue(double Jout, double cmax, int al_it, int al_tot) {
+        constexpr int n = C::n, m = C::m;
+        const int N = P.N;
         if (lane == 0) {
             TOResult r;
             r.J = Jout; r.c_max = cmax; r.iterations_total = al_tot; r.iterations_outer = al_it;
@@ -1371,6 +1363,29 @@ struct Solver {
         }
         __syncwarp();
     }
+
+    // ---- load one problem into the workspace, solve, write results ----
+    __device__ void run(int b_) {
+        prologue(b_);
+        const int N = P.N;
+        al_on = false;
+        double Jout = 0.0, cmax = 0.0;
+        int al_it = 0, al_tot = 0;
+        bool ok;
+        if (ctl.mode == 0) {
+            const size_t nk = (size_t)(N - 1) * C::KDS;
+            for (size_t e = lane; e < nk; e += 32) ws[L.KD + e] = 0.0;
+            __syncwarp();
+            outer_idx = 0;
+            ok = ilqr_solve();
+            Jout = last_cost;
+            al_tot = iterations;
+        } else {
+            ok = al_solve(Jout, cmax, al_it, al_tot);
+        }
+        (void)ok;
+        epilogue(Jout, cmax, al_it, al_tot);
+    }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1401,15 +1416,4 @@ template <class C> int max_blocks_fn() {
 template <class C> void launch_fn(int grid, cudaStream_t st, const DevProblem& P, const DevBatch& B, const DevCtl& c) {
     solve_kernel<C><<<grid, 32, 0, st>>>(P, B, c);
 }
-template <class C> KernelInfo make_info() {
-    KernelInfo k;
-    k.model = C::MODEL; k.integ = C::INTEG; k.inf = C::INF; k.mt = C::MT; k.n = C::n; k.m = C::m;
-    k.smem_bytes = sizeof(Smem<C>);
-    k.ws_doubles = ws_doubles_fn<C>;
-    k.debug_doubles = debug_doubles_fn<C>;
-    k.max_blocks_per_sm = max_blocks_fn<C>;
-    k.launch = launch_fn<C>;
-    return k;
-}
-
 }  // namespace tob

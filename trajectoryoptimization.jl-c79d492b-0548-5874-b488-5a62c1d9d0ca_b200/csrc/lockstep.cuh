@@ -1,0 +1,1281 @@
+// B200 engine, throughput path: the batch advances in LOCKSTEP, one iLQR iteration ("tick") at a
+// time, through phase kernels that each use the parallelism natural to their phase:
+//
+//   ls_jac_kernel     thread per (problem, knot, partial-chunk): dual-number rk3 Jacobians        (src/model.jl:491-512)
+//   ls_bp_kernel      a GROUP of GS lanes per problem (2 problems per warp for the quadrotor):
+//                     lane j owns column j of S, A, Qxx, Qux, K in REGISTERS; the left operands
+//                     (A, B, T, Tu, K, KQ) stream from shared memory as broadcast loads; every
+//                     inner product is the same sequential FMA chain as in the oracle           (backward_pass.jl:9-85)
+//   ls_trial_kernel   thread per (problem, step size): closed-loop rk3 rollout + AL cost, G step
+//                     sizes per launch, first accepted wins; unaccepted problems go to a retry
+//                     list for the next G step sizes                                             (forward_pass.jl:5-85)
+//   ls_accept_kernel  thread per problem: re-rolls the accepted step in place (X <- X̄, U <- Ū),
+//                     Todorov gradient, iteration record, convergence tests                      (ilqr_methods.jl:30-45,77-162)
+//   ls_outer_kernel   warp per problem whose inner solve ended this tick: AL dual / penalty /
+//                     active-set update, outer convergence, start of the next inner solve        (augmented_lagrangian_methods.jl:2-126)
+//
+// Problems leave the active list when they finish (ragged iteration counts), so every tick only
+// touches live problems; the host just replays the tick until the list is empty.  Per-problem
+// arithmetic is identical to the warp-persistent engine (engine.cuh) and to the CPU oracle: the
+// assignment of work to lanes differs, the expression trees do not.
+#pragma once
+#include "engine.cuh"
+
+namespace tob {
+
+template <class C> __host__ __device__ constexpr int ls_group_size() {
+    return (C::n > 8 || C::m > 8) ? 16 : ((C::n > 4 || C::m > 4) ? 8 : 4);
+}
+
+// ------------------------------------------------------------------------------------------
+// warp-level slow path: everything that is not the per-iteration hot loop reuses Solver<C>
+// ------------------------------------------------------------------------------------------
+template <class C>
+struct LsSolver : Solver<C> {
+    typedef Solver<C> S_;
+    LsState* st;
+    int outer_i, al_iterations, al_total, inner_i;
+    double J_prev, Jout, cmax_out;
+
+    __device__ LsSolver(const DevProblem& P_, const DevBatch& B_, const DevCtl& c_, Smem<C>& s_, double* ws_, int lane_)
+        : S_(P_, B_, c_, s_, ws_, lane_, false) {}
+
+    __device__ void load(LsState* s, int b_) {
+        st = s;
+        this->b = b_;
+        this->load_x0();
+        this->io = this->ctl.o.opts_uncon;
+        this->io.cost_tolerance = s->cost_tol;
+        this->io.gradient_norm_tolerance = s->grad_tol;
+        this->al_on = (this->ctl.mode == 1);
+        this->rho = s->rho; this->drho = s->drho;
+        this->iterations = s->iterations; this->dJ_zero = s->dJ_zero; this->steps = s->steps; this->status = s->status;
+        this->last_dJ = s->last_dJ; this->last_grad = s->last_grad; this->last_cost = s->last_cost;
+        this->fp_expected = s->fp_expected; this->fp_z = s->fp_z; this->fp_alpha = s->fp_alpha;
+        this->outer_idx = (s->outer_i > 0) ? s->outer_i - 1 : 0;
+        this->n_inner_rec = s->n_inner_rec; this->n_outer_rec = s->n_outer_rec;
+        this->ls_count = s->ls_count;
+        outer_i = s->outer_i; al_iterations = s->al_iterations; al_total = s->al_total; inner_i = s->inner_i;
+        J_prev = s->J_prev; Jout = s->Jout; cmax_out = s->cmax;
+    }
+    __device__ void store() {
+        if (this->lane == 0) {
+            LsState* s = st;
+            s->cost_tol = this->io.cost_tolerance; s->grad_tol = this->io.gradient_norm_tolerance;
+            s->rho = this->rho; s->drho = this->drho;
+            s->iterations = this->iterations; s->dJ_zero = this->dJ_zero; s->steps = this->steps; s->status = this->status;
+            s->last_dJ = this->last_dJ; s->last_grad = this->last_grad; s->last_cost = this->last_cost;
+            s->fp_expected = this->fp_expected; s->fp_z = this->fp_z; s->fp_alpha = this->fp_alpha;
+            s->n_inner_rec = this->n_inner_rec; s->n_outer_rec = this->n_outer_rec;
+            s->ls_count = this->ls_count;
+            s->outer_i = outer_i; s->al_iterations = al_iterations; s->al_total = al_total; s->inner_i = inner_i;
+            s->J_prev = J_prev; s->Jout = Jout; s->cmax = cmax_out;
+            s->winner = -1;
+        }
+        __syncwarp();
+    }
+
+    // first part of ilqr_solve (ilqr_methods.jl:3-20): reset, rollout, initial cost and record
+    __device__ void begin_inner() {
+        this->iterations = 0; this->dJ_zero = 0; this->rho = 0.0; this->drho = 0.0;
+        this->fp_expected = 0.0; this->fp_z = 0.0; this->fp_alpha = 0.0;
+        if (!this->all_finite_X()) this->rollout_open(false);
+        J_prev = this->eval_cost();
+        this->record_inner(J_prev, __longlong_as_double(0x7ff0000000000000LL));
+        inner_i = 1;
+    }
+    __device__ void set_tolerances() {  // augmented_lagrangian_methods.jl:39-50
+        const TOALOptions& o = this->ctl.o;
+        if (outer_i != o.iterations) {
+            this->io.cost_tolerance = o.cost_tolerance_intermediate;
+            this->io.gradient_norm_tolerance = o.gradient_norm_tolerance_intermediate;
+        } else {
+            this->io.cost_tolerance = o.cost_tolerance;
+            this->io.gradient_norm_tolerance = o.gradient_norm_tolerance;
+        }
+    }
+    __device__ void finish() {
+        if (this->ctl.mode == 0) this->epilogue(this->last_cost, 0.0, 0, this->iterations);
+        else this->epilogue(Jout, cmax_out, al_iterations, al_total);
+    }
+    __device__ double max_penalty_lex() {  // maximum(maximum(mu)) over a vector of vectors (Q20)
+        double pm = 0.0;
+        const DevProblem& P = this->P;
+        if (this->lane == 0) {
+            int best = -1;
+            for (int k = 0; k < P.N; k++) {
+                if (best < 0) { best = k; continue; }
+                const int ca = P.knot_row_count[best], cb_ = P.knot_row_count[k];
+                const double* a = this->mu() + P.knot_lam_off[best];
+                const double* c = this->mu() + P.knot_lam_off[k];
+                bool less = false, decided = false;
+                for (int q = 0; q < ca && q < cb_; q++) {
+                    if (a[q] < c[q]) { less = true; decided = true; break; }
+                    if (c[q] < a[q]) { decided = true; break; }
+                }
+                if (!decided) less = ca < cb_;
+                if (less) best = k;
+            }
+            if (best >= 0 && P.knot_row_count[best] > 0) {
+                const double* a = this->mu() + P.knot_lam_off[best];
+                pm = a[0];
+                for (int q = 1; q < P.knot_row_count[best]; q++) pm = dmax(pm, a[q]);
+            }
+        }
+        return bcast(pm, 0);
+    }
+
+    // problem start.  Returns true if the problem needs iLQR steps (goes on the active list).
+    __device__ bool start(int b_) {
+        const DevProblem& P = this->P;
+        const TOALOptions& o = this->ctl.o;
+        this->prologue(b_);
+        const size_t nk = (size_t)(P.N - 1) * C::KDS;
+        for (size_t e = this->lane; e < nk; e += 32) this->ws[this->L.KD + e] = 0.0;
+        __syncwarp();
+        al_iterations = 0; al_total = 0; Jout = 0.0; cmax_out = 0.0; outer_i = 0; inner_i = 0; J_prev = 0.0;
+        this->fp_expected = 0.0; this->fp_z = 0.0; this->fp_alpha = 0.0;
+        this->rho = 0.0; this->drho = 0.0; this->iterations = 0; this->dJ_zero = 0;
+        this->outer_idx = 0;
+        if (this->ctl.mode == 0) {
+            this->al_on = false;
+            begin_inner();
+            if (this->io.iterations >= 1) return true;
+            finish();
+            return false;
+        }
+        // al_solve prologue (augmented_lagrangian_methods.jl:2-15)
+        this->al_on = true;
+        for (int e = this->lane; e < P.Ptot; e += 32) { this->lam()[e] = 0.0; this->mu()[e] = o.penalty_initial; }
+        __syncwarp();
+        if (!this->all_finite_X()) this->rollout_open(false);
+        const double J0 = this->eval_cost();
+        const double cmax = this->max_violation();
+        this->record_outer(J0, cmax, al_iterations, al_total);
+        Jout = J0; cmax_out = cmax;
+        if (o.iterations < 1) {
+            this->status |= TO_STATUS_MAX_OUTER;
+            finish();
+            return false;
+        }
+        outer_i = 1;
+        this->outer_idx = 0;
+        set_tolerances();
+        begin_inner();
+        if (this->io.iterations >= 1) return true;
+        return after_inner(true);
+    }
+
+    // the inner solve of this problem ended (ok = false: the reference would have thrown).
+    // Returns true if another inner solve was started.
+    __device__ bool after_inner(bool ok) {
+        const TOALOptions& o = this->ctl.o;
+        for (;;) {
+            if (this->ctl.mode == 0 || !ok) { finish(); return false; }
+            // rest of step! (augmented_lagrangian_methods.jl:53-67), record, convergence
+            const double J = this->eval_cost();
+            const double cmax = this->max_violation();
+            this->dual_penalty_update();
+            this->record_outer(J, cmax, al_iterations, al_total);
+            Jout = J; cmax_out = cmax;
+            bool converged = false;
+            if (o.kickout_max_penalty) converged = (max_penalty_lex() == o.penalty_max);
+            converged = converged || (cmax < o.constraint_tolerance);
+            if (converged) { finish(); return false; }
+            this->iterations = 0; this->dJ_zero = 0; this->rho = 0.0; this->drho = 0.0;
+            outer_i += 1;
+            if (outer_i > o.iterations) {
+                this->status |= TO_STATUS_MAX_OUTER;
+                finish();
+                return false;
+            }
+            this->outer_idx = outer_i - 1;
+            set_tolerances();
+            begin_inner();
+            if (this->io.iterations >= 1) return true;
+            ok = true;  // an inner solve with zero allowed steps ends immediately
+        }
+    }
+};
+
+__device__ __forceinline__ void ls_append(int* list, unsigned int* count, int b) {
+    const unsigned int pos = atomicAdd(count, 1u);
+    list[pos] = b;
+}
+
+// ---- init: prologue + first inner-solve setup for every problem of the batch ----------------
+template <class C>
+__global__ void __launch_bounds__(32) ls_init_kernel(const DevProblem P, const DevBatch Bt, const DevCtl ctl, const LsCtl lc) {
+    __shared__ Smem<C> sm;
+    const int lane = threadIdx.x;
+    for (int b = blockIdx.x; b < Bt.B; b += gridDim.x) {
+        LsSolver<C> s(P, Bt, ctl, sm, lc.ws + (size_t)b * lc.ws_stride, lane);
+        s.st = &lc.st[b];
+        const bool active = s.start(b);
+        s.store();
+        if (active && lane == 0) ls_append(lc.list[0], &lc.counts[0], b);
+    }
+}
+
+// ---- outer: problems whose inner solve ended in this tick ------------------------------------
+template <class C>
+__global__ void __launch_bounds__(32) ls_outer_kernel(const DevProblem P, const DevBatch Bt, const DevCtl ctl, const LsCtl lc, const int cur) {
+    __shared__ Smem<C> sm;
+    const int lane = threadIdx.x;
+    const unsigned int n = lc.counts[4];
+    for (unsigned int a = blockIdx.x; a < n; a += gridDim.x) {
+        const int b = lc.outer_list[a];
+        LsSolver<C> s(P, Bt, ctl, sm, lc.ws + (size_t)b * lc.ws_stride, lane);
+        s.load(&lc.st[b], b);
+        const bool active = s.after_inner(lc.st[b].inner_ok != 0);
+        s.store();
+        if (active && lane == 0) ls_append(lc.list[cur ^ 1], &lc.counts[cur ^ 1], b);
+    }
+}
+
+// ---- Jacobians: thread per (problem, knot, chunk of partial directions) -----------------------
+template <class C>
+__global__ void __launch_bounds__(128) ls_jac_kernel(const DevProblem P, const LsCtl lc, const int cur) {
+    constexpr int PC = C::PC;
+    typedef Dual<PC> D;
+    const unsigned int na = lc.counts[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { lc.counts[cur ^ 1] = 0; lc.counts[2] = 0; lc.counts[3] = 0; lc.counts[4] = 0; }
+    const int N = P.N;
+    const unsigned int per = (unsigned int)(N - 1) * C::NCH;
+    const unsigned long long items = (unsigned long long)na * per;
+    const WsLayout L = ws_layout<C>(N, P.Ptot, false);
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < items; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned int a = (unsigned int)(t / per), it = (unsigned int)(t - (unsigned long long)a * per);
+        const int b = lc.list[cur][a];
+        double* ws = lc.ws + (size_t)b * lc.ws_stride;
+        const int k = it / C::NCH, ch = it - k * C::NCH;
+        const int s0 = ch * PC;
+        D xs[C::n0], us[C::m0], dts, xn[C::n0];
+        const double* xk = ws + L.X + (size_t)k * C::n;
+        const double* uk = ws + L.U + (size_t)k * C::m;
+#pragma unroll
+        for (int i = 0; i < C::n0; i++) {
+            xs[i] = D(xk[i]);
+#pragma unroll
+            for (int j = 0; j < PC; j++) if (s0 + j == i) xs[i].p[j] = 1.0;
+        }
+#pragma unroll
+        for (int i = 0; i < C::m0; i++) {
+            us[i] = D(uk[i]);
+#pragma unroll
+            for (int j = 0; j < PC; j++) if (s0 + j == C::n0 + i) us[i].p[j] = 1.0;
+        }
+        double dt = P.dt;
+        if constexpr (C::MT) {
+            const double h = uk[C::m - 1];
+            dt = h * h;
+        }
+        dts = D(dt);
+        if constexpr (C::MT) {
+#pragma unroll
+            for (int j = 0; j < PC; j++) if (s0 + j == C::n0 + C::m0) dts.p[j] = 1.0;
+        }
+        fd_model<C::MODEL, C::INTEG, D>(xn, xs, us, dts);
+        double* z = ws + L.Z + (size_t)k * C::ZS;
+#pragma unroll
+        for (int j = 0; j < PC; j++) {
+            if (s0 + j < C::PT) {
+#pragma unroll
+                for (int i = 0; i < C::n0; i++) z[(s0 + j) * C::n0 + i] = xn[i].p[j];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward pass: GS lanes per problem, lane j owns column j
+// ------------------------------------------------------------------------------------------
+template <class C>
+struct BpSmem {
+    double A[C::n * C::n], B[C::n * C::m];
+    double T[C::n * C::n], Tu[C::m * C::n];
+    double K[C::m * C::n], Qux[C::m * C::n], Quu[C::m * C::m], KQ[C::n * C::m];
+    double Sx[C::n], Qu[C::m], d[C::m], xk[C::n], uk[C::m], vQx[C::nq], vQu[C::mq];
+};
+
+template <class C>
+struct BpGroup {
+    static constexpr int n = C::n, m = C::m, n0 = C::n0, m0 = C::m0, nq = C::nq, mq = C::mq;
+    static constexpr int GS = ls_group_size<C>();
+    static constexpr int DL = (n < GS) ? n : 0;  // lane that solves for the feed-forward term d
+    const DevProblem& P;
+    BpSmem<C>& sm;
+    double* ws;
+    const WsLayout L;
+    const int j;            // lane within the group
+    const unsigned gmask;   // lanes of this group
+    const bool al_on;
+    TOiLQROptions io;
+    double rho, drho;
+    // register-resident columns
+    double Scol[n], Acol[n], Bcol[n], Qxxc[n], Quxc[m], Quuc[m], Kcol[m];
+    double Qx_j, Qu_j, Sx_j;
+
+    __device__ BpGroup(const DevProblem& P_, BpSmem<C>& s_, double* ws_, int j_, unsigned gmask_, bool al_on_, const TOiLQROptions& io_)
+        : P(P_), sm(s_), ws(ws_), L(ws_layout<C>(P_.N, P_.Ptot, false)), j(j_), gmask(gmask_), al_on(al_on_), io(io_) {}
+
+    __device__ void gsync() { __syncwarp(gmask); }
+    __device__ const double* X(int k) { return ws + L.X + (size_t)k * n; }
+    __device__ const double* U(int k) { return ws + L.U + (size_t)k * m; }
+
+    __device__ void reg_update(bool increase) {  // ilqr_methods.jl:164-176
+        const double f = io.bp_reg_increase_factor;
+        if (increase) {
+            drho = dmax(drho * f, f);
+            rho = dmax(rho * drho, io.bp_reg_min);
+        } else {
+            drho = dmin(drho / f, 1.0 / f);
+            rho = rho * drho * ((rho * drho > io.bp_reg_min) ? 1.0 : 0.0);
+        }
+    }
+
+    // columns j of A_k, B_k of the augmented model -> registers + shared memory
+    __device__ void load_AB(int k) {
+        const double* z = ws + L.Z + (size_t)k * C::ZS;
+        if (j < n) {
+#pragma unroll
+            for (int i = 0; i < n; i++) {
+                const double v = (i < n0 && j < n0) ? z[j * n0 + i] : 0.0;
+                Acol[i] = v;
+                sm.A[j * n + i] = v;
+            }
+        }
+        if (j < m) {
+            double h2 = 0.0;
+            if constexpr (C::MT) h2 = 2.0 * U(k)[m - 1];
+#pragma unroll
+            for (int i = 0; i < n; i++) {
+                double v = 0.0;
+                if (j < m0) {
+                    if (i < n0) v = z[(n0 + j) * n0 + i];
+                } else if (C::INF && j < m0 + n0) {
+                    v = (i == j - m0) ? 1.0 : 0.0;
+                } else if (C::MT && j == m - 1) {
+                    if (i < n0) v = z[(n0 + m0) * n0 + i] * h2;
+                    else if (i == n - 1) v = 1.0;
+                }
+                Bcol[i] = v;
+                sm.B[j * n + i] = v;
+            }
+        }
+    }
+
+    // cost expansion of knot k (+ AL terms), column j -> registers
+    // (src/cost.jl:183-198, minimum_time.jl:161-204, augmented_lagrangian_methods.jl:186-229)
+    __device__ void expansion(int k) {
+        const int N = P.N;
+        const bool term = (k == N - 1);
+        if (j < n) sm.xk[j] = X(k)[j];
+        if (j < m) sm.uk[j] = term ? 0.0 : U(k)[j];
+        gsync();
+        double x[n], u[m];
+#pragma unroll
+        for (int i = 0; i < n; i++) x[i] = sm.xk[i];
+#pragma unroll
+        for (int i = 0; i < m; i++) u[i] = sm.uk[i];
+        const double* Qm = term ? P.Qf : P.Q;
+        const double* qv = term ? P.qf : P.q;
+        const bool qd = term ? P.qf_diag : P.q_diag;
+        if (j < nq) {
+            double a = 0.0, bq = 0.0;
+            if (qd) {
+#pragma unroll
+                for (int i = 0; i < nq; i++) if (i == j) a = fma(__ldg(&Qm[i * nq + i]), x[i], a);
+            } else {
+#pragma unroll
+                for (int i = 0; i < nq; i++) a = fma(__ldg(&Qm[i * nq + j]), x[i], a);
+            }
+            if (!term && !P.h_zero) {
+#pragma unroll
+                for (int i = 0; i < mq; i++) bq = fma(__ldg(&P.H[j * mq + i]), u[i], bq);
+            }
+            sm.vQx[j] = term ? (a + __ldg(&qv[j])) : ((a + __ldg(&qv[j])) + bq);
+        }
+        if (!term && j < mq) {
+            double a = 0.0, bq = 0.0;
+            if (P.r_diag) {
+#pragma unroll
+                for (int i = 0; i < mq; i++) if (i == j) a = fma(__ldg(&P.R[i * mq + i]), u[i], a);
+            } else {
+#pragma unroll
+                for (int i = 0; i < mq; i++) a = fma(__ldg(&P.R[i * mq + j]), u[i], a);
+            }
+            if (!P.h_zero) {
+#pragma unroll
+                for (int i = 0; i < nq; i++) bq = fma(__ldg(&P.H[i * mq + j]), x[i], bq);
+            }
+            sm.vQu[j] = (a + __ldg(&P.r[j])) + bq;
+        }
+        gsync();
+        double dt = P.dt, tau = 0.0, l1 = 0.0;
+        if (C::MT && !term) {
+            tau = u[m - 1];
+            dt = tau * tau;
+            l1 = quad_stage<C>(P, x, u);
+        }
+        // base blocks, column j
+        if (j < n) {
+#pragma unroll
+            for (int i = 0; i < n; i++) {
+                double v = 0.0;
+                if (i < nq && j < nq) v = term ? __ldg(&Qm[j * nq + i]) : __ldg(&Qm[j * nq + i]) * dt;
+                if (C::MT && i == n - 1 && j == n - 1) v = P.R_mt;
+                Qxxc[i] = v;
+            }
+            double v = 0.0;
+            if (j < nq) v = term ? sm.vQx[j] : sm.vQx[j] * dt;
+            if (C::MT && j == n - 1) v = P.R_mt * x[n - 1];
+            Qx_j = v;
+            if (!term) {
+#pragma unroll
+                for (int i = 0; i < m; i++) {  // ux is m×n, element (i,j)
+                    double w = 0.0;
+                    if (i < mq && j < nq) w = P.h_zero ? (0.0 * dt) : __ldg(&P.H[j * mq + i]) * dt;
+                    if (C::MT && i == m - 1 && j < nq) w = (2.0 * tau) * sm.vQx[j];
+                    Quxc[i] = w;
+                }
+            }
+        }
+        if (!term && j < m) {
+#pragma unroll
+            for (int i = 0; i < m; i++) {
+                double v = 0.0;
+                if (i < mq && j < mq) v = __ldg(&P.R[j * mq + i]) * dt;
+                if (C::MT) {
+                    if (j == m - 1 && i < mq) v = (2.0 * tau) * sm.vQu[i];
+                    if (i == m - 1 && j < mq) v = (2.0 * tau) * sm.vQu[j];
+                    if (i == m - 1 && j == m - 1) v = 2.0 * l1 + P.R_mt;
+                }
+                Quuc[i] = v;
+            }
+            double v = 0.0;
+            if (j < mq) v = sm.vQu[j] * dt;
+            if (C::MT && j == m - 1) v = tau * (2.0 * l1 + P.R_mt);
+            Qu_j = v;
+        }
+        if (!al_on) return;
+        const int rb = P.knot_row_begin[k], rc = P.knot_row_count[k], lo = P.knot_lam_off[k];
+        if (rc == 0) return;
+        const double* lamk = ws + L.LAM + lo;
+        const double* muk = ws + L.MU + lo;
+        double axx[n], aux_[m], auu[m], ax = 0.0, au = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; i++) axx[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < m; i++) { aux_[i] = 0.0; auu[i] = 0.0; }
+        for (int r_ = 0; r_ < rc; r_++) {
+            const DevRow r = P.rows[rb + r_];
+            const double gx = (j < n) ? row_jac<C>(r, x, j) : 0.0;
+            const double gu = (!term && j < m) ? row_jac<C>(r, x, n + j) : 0.0;
+            if (gx != 0.0 || gu != 0.0) {
+                const double c = row_value<C>(r, x, u);
+                const double lam_r = lamk[r_];
+                const bool act = r.eq ? true : ((c >= 0.0) || (lam_r > 0.0));
+                const double im = act ? muk[r_] : 0.0;
+                const double g = im * c + lam_r;
+                if (gx != 0.0) {
+#pragma unroll
+                    for (int i = 0; i < n; i++) {
+                        const double gi = row_jac<C>(r, x, i);
+                        if (gi != 0.0) axx[i] = fma(gi * im, gx, axx[i]);
+                    }
+                    if (!term) {
+#pragma unroll
+                        for (int i = 0; i < m; i++) {
+                            const double gi = row_jac<C>(r, x, n + i);
+                            if (gi != 0.0) aux_[i] = fma(gi * im, gx, aux_[i]);
+                        }
+                    }
+                    ax = fma(gx, g, ax);
+                }
+                if (gu != 0.0) {
+#pragma unroll
+                    for (int i = 0; i < m; i++) {
+                        const double gi = row_jac<C>(r, x, n + i);
+                        if (gi != 0.0) auu[i] = fma(gi * im, gu, auu[i]);
+                    }
+                    au = fma(gu, g, au);
+                }
+            }
+        }
+        if (j < n) {
+#pragma unroll
+            for (int i = 0; i < n; i++) Qxxc[i] += axx[i];
+            Qx_j += ax;
+            if (!term) {
+#pragma unroll
+                for (int i = 0; i < m; i++) Quxc[i] += aux_[i];
+            }
+        }
+        if (!term && j < m) {
+#pragma unroll
+            for (int i = 0; i < m; i++) Quuc[i] += auu[i];
+            Qu_j += au;
+        }
+    }
+
+    // Q trajectory (restart quirk Q1): layout per knot [Qx(n) Qu(m) Qxx(n*n) Quu(m*m) Qux(m*n)]
+    __device__ void q_store(int k) {
+        double* q = ws + L.QST + (size_t)k * C::QS;
+        if (j < n) {
+            q[j] = Qx_j;
+#pragma unroll
+            for (int i = 0; i < n; i++) q[n + m + j * n + i] = Qxxc[i];
+#pragma unroll
+            for (int i = 0; i < m; i++) q[n + m + n * n + m * m + j * m + i] = Quxc[i];
+        }
+        if (j < m) {
+            q[n + j] = Qu_j;
+#pragma unroll
+            for (int i = 0; i < m; i++) q[n + m + n * n + j * m + i] = Quuc[i];
+        }
+    }
+    __device__ void q_load(int k) {
+        const double* q = ws + L.QST + (size_t)k * C::QS;
+        if (j < n) {
+            Qx_j = q[j];
+#pragma unroll
+            for (int i = 0; i < n; i++) Qxxc[i] = q[n + m + j * n + i];
+#pragma unroll
+            for (int i = 0; i < m; i++) Quxc[i] = q[n + m + n * n + m * m + j * m + i];
+        }
+        if (j < m) {
+            Qu_j = q[n + j];
+#pragma unroll
+            for (int i = 0; i < m; i++) Quuc[i] = q[n + m + n * n + j * m + i];
+        }
+    }
+
+    // isposdef(Hermitian(A)) — same code as Solver::chol_pd
+    __device__ bool chol_pd(const double* Areg) {
+        double Uc[m * m];
+#pragma unroll
+        for (int c = 0; c < m; c++) {
+#pragma unroll
+            for (int i = 0; i < c; i++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int l = 0; l < i; l++) acc = fma(Uc[i * m + l], Uc[c * m + l], acc);
+                Uc[c * m + i] = (Areg[c * m + i] - acc) / Uc[i * m + i];
+            }
+            double acc = 0.0;
+#pragma unroll
+            for (int l = 0; l < c; l++) acc = fma(Uc[c * m + l], Uc[c * m + l], acc);
+            const double dd = Areg[c * m + c] - acc;
+            if (!(dd > 0.0)) return false;
+            Uc[c * m + c] = sqrt(dd);
+        }
+        return true;
+    }
+    struct LU {
+        double a[m * m];
+        int piv[m];
+        bool tril_only, triu;
+    };
+    __device__ void lu_factor(LU& f) {  // same code as Solver::lu_factor (Julia's dense `\`)
+        bool tril = true, triu = true;
+#pragma unroll
+        for (int c = 0; c < m; c++)
+#pragma unroll
+            for (int i = 0; i < m; i++) {
+                if (i < c && f.a[c * m + i] != 0.0) tril = false;
+                if (i > c && f.a[c * m + i] != 0.0) triu = false;
+            }
+        f.triu = triu;
+        f.tril_only = tril && !triu;
+#pragma unroll
+        for (int c = 0; c < m; c++) f.piv[c] = c;
+        if (triu || f.tril_only) return;
+#pragma unroll
+        for (int c = 0; c < m; c++) {
+#pragma unroll
+            for (int i = 0; i < c; i++) {
+#pragma unroll
+                for (int q = i + 1; q < m; q++) {
+                    const bool sw = (f.piv[i] == q);
+                    const double t0 = f.a[c * m + i], t1 = f.a[c * m + q];
+                    f.a[c * m + i] = sw ? t1 : t0;
+                    f.a[c * m + q] = sw ? t0 : t1;
+                }
+            }
+#pragma unroll
+            for (int i = 1; i < c; i++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int l = 0; l < i; l++) acc = fma(f.a[l * m + i], f.a[c * m + l], acc);
+                f.a[c * m + i] = f.a[c * m + i] - acc;
+            }
+#pragma unroll
+            for (int i = c; i < m; i++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int l = 0; l < c; l++) acc = fma(f.a[l * m + i], f.a[c * m + l], acc);
+                f.a[c * m + i] = f.a[c * m + i] - acc;
+            }
+            int p = c;
+            double amax = fabs(f.a[c * m + c]);
+#pragma unroll
+            for (int i = c + 1; i < m; i++)
+                if (fabs(f.a[c * m + i]) > amax) { amax = fabs(f.a[c * m + i]); p = i; }
+            f.piv[c] = p;
+#pragma unroll
+            for (int q = c + 1; q < m; q++) {
+                const bool sw = (p == q);
+#pragma unroll
+                for (int cc = 0; cc <= c; cc++) {
+                    const double t0 = f.a[cc * m + c], t1 = f.a[cc * m + q];
+                    f.a[cc * m + c] = sw ? t1 : t0;
+                    f.a[cc * m + q] = sw ? t0 : t1;
+                }
+            }
+            const double rp = 1.0 / f.a[c * m + c];
+#pragma unroll
+            for (int i = c + 1; i < m; i++) f.a[c * m + i] = f.a[c * m + i] * rp;
+        }
+    }
+    __device__ void lu_solve(const LU& f, double* bv) {
+        if (f.tril_only) {
+#pragma unroll
+            for (int i = 0; i < m; i++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int l = 0; l < i; l++) acc = fma(f.a[l * m + i], bv[l], acc);
+                bv[i] = (bv[i] - acc) / f.a[i * m + i];
+            }
+            return;
+        }
+        if (!f.triu) {
+#pragma unroll
+            for (int i = 0; i < m; i++) {
+#pragma unroll
+                for (int q = i + 1; q < m; q++) {
+                    const bool sw = (f.piv[i] == q);
+                    const double t0 = bv[i], t1 = bv[q];
+                    bv[i] = sw ? t1 : t0;
+                    bv[q] = sw ? t0 : t1;
+                }
+            }
+#pragma unroll
+            for (int i = 1; i < m; i++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int l = 0; l < i; l++) acc = fma(f.a[l * m + i], bv[l], acc);
+                bv[i] = bv[i] - acc;
+            }
+        }
+#pragma unroll
+        for (int i = m - 1; i >= 0; i--) {
+            double acc = 0.0;
+#pragma unroll
+            for (int l = i + 1; l < m; l++) acc = fma(f.a[l * m + i], bv[l], acc);
+            bv[i] = (bv[i] - acc) / f.a[i * m + i];
+        }
+    }
+
+    // the whole backward pass of one problem, including regularisation restarts
+    __device__ void run(double& dV0, double& dV1) {
+        const int N = P.N;
+        bool store_mode = false;
+        int stored_from = N - 1;
+        for (;;) {
+            // terminal cost-to-go: S = Qxx_N, Sx = Qx_N
+            expansion(N - 1);
+            if (j < n) {
+#pragma unroll
+                for (int i = 0; i < n; i++) Scol[i] = Qxxc[i];
+                sm.Sx[j] = Qx_j;
+            }
+            dV0 = 0.0;
+            dV1 = 0.0;
+            bool failed = false;
+            gsync();
+            for (int k = N - 2; k >= 0; k--) {
+                load_AB(k);
+                if (store_mode && k >= stored_from) {
+                    q_load(k);
+                    gsync();
+                } else {
+                    expansion(k);
+                    gsync();
+                }
+                // Qx += A'Sx ; Qu += B'Sx
+                if (j < n) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < n; l++) acc = fma(Acol[l], sm.Sx[l], acc);
+                    Qx_j += acc;
+                }
+                if (j < m) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < n; l++) acc = fma(Bcol[l], sm.Sx[l], acc);
+                    Qu_j += acc;
+                }
+                // T = A'S (column j), Tu = B'S (column j)
+                if (j < n) {
+#pragma unroll
+                    for (int i = 0; i < n; i++) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < n; l++) acc = fma(sm.A[i * n + l], Scol[l], acc);
+                        sm.T[j * n + i] = acc;
+                    }
+#pragma unroll
+                    for (int i = 0; i < m; i++) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < n; l++) acc = fma(sm.B[i * n + l], Scol[l], acc);
+                        sm.Tu[j * m + i] = acc;
+                    }
+                }
+                gsync();
+                // Qxx += T*A ; Qux += Tu*A ; Quu += Tu*B
+                if (j < n) {
+#pragma unroll
+                    for (int i = 0; i < n; i++) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < n; l++) acc = fma(sm.T[l * n + i], Acol[l], acc);
+                        Qxxc[i] += acc;
+                    }
+#pragma unroll
+                    for (int i = 0; i < m; i++) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < n; l++) acc = fma(sm.Tu[l * m + i], Acol[l], acc);
+                        Quxc[i] += acc;
+                    }
+                }
+                if (j < m) {
+#pragma unroll
+                    for (int i = 0; i < m; i++) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < n; l++) acc = fma(sm.Tu[l * m + i], Bcol[l], acc);
+                        Quuc[i] += acc;
+                    }
+                }
+                if (store_mode) {
+                    q_store(k);
+                    if (k < stored_from) stored_from = k;
+                }
+                // publish Quu, Qux, Qu
+                if (j < m) {
+#pragma unroll
+                    for (int i = 0; i < m; i++) sm.Quu[j * m + i] = Quuc[i];
+                    sm.Qu[j] = Qu_j;
+                }
+                if (j < n) {
+#pragma unroll
+                    for (int i = 0; i < m; i++) sm.Qux[j * m + i] = Quxc[i];
+                }
+                gsync();
+                // Quu_reg = Quu + rho*I, replicated per lane
+                double Quu[m * m];
+                LU f;
+#pragma unroll
+                for (int e = 0; e < m * m; e++) { Quu[e] = sm.Quu[e]; f.a[e] = Quu[e]; }
+#pragma unroll
+                for (int i = 0; i < m; i++) f.a[i * m + i] = Quu[i * m + i] + rho * 1.0;
+                if (!chol_pd(f.a)) { failed = true; break; }
+                lu_factor(f);
+                if (j < n) {
+                    double rhs[m];
+#pragma unroll
+                    for (int i = 0; i < m; i++) rhs[i] = Quxc[i];
+                    lu_solve(f, rhs);
+#pragma unroll
+                    for (int i = 0; i < m; i++) {
+                        Kcol[i] = -1.0 * rhs[i];
+                        sm.K[j * m + i] = Kcol[i];
+                    }
+                }
+                if (j == DL) {
+                    double rhs[m];
+#pragma unroll
+                    for (int i = 0; i < m; i++) rhs[i] = sm.Qu[i];
+                    lu_solve(f, rhs);
+#pragma unroll
+                    for (int i = 0; i < m; i++) sm.d[i] = -1.0 * rhs[i];
+                }
+                gsync();
+                double dk[m], Quv[m];
+#pragma unroll
+                for (int i = 0; i < m; i++) { dk[i] = sm.d[i]; Quv[i] = sm.Qu[i]; }
+                {   // publish K, d for the rollouts
+                    double* kd = ws + L.KD + (size_t)k * C::KDS;
+                    if (j < n) {
+#pragma unroll
+                        for (int i = 0; i < m; i++) kd[j * m + i] = Kcol[i];
+                    }
+                    if (j == DL) {
+#pragma unroll
+                        for (int i = 0; i < m; i++) kd[m * n + i] = dk[i];
+                    }
+                }
+                // KQ = K'Quu (row j), S.x
+                if (j < n) {
+                    double KQr[m];
+#pragma unroll
+                    for (int c = 0; c < m; c++) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < m; l++) acc = fma(Kcol[l], Quu[c * m + l], acc);
+                        KQr[c] = acc;
+                        sm.KQ[c * n + j] = acc;
+                    }
+                    double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                    for (int l = 0; l < m; l++) a1 = fma(KQr[l], dk[l], a1);
+#pragma unroll
+                    for (int l = 0; l < m; l++) a2 = fma(Kcol[l], Quv[l], a2);
+#pragma unroll
+                    for (int l = 0; l < m; l++) a3 = fma(Quxc[l], dk[l], a3);
+                    Sx_j = ((Qx_j + a1) + a2) + a3;
+                }
+                gsync();
+                // unsymmetrised S.xx, column j -> T
+                if (j < n) {
+#pragma unroll
+                    for (int i = 0; i < n; i++) {
+                        double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                        for (int l = 0; l < m; l++) a1 = fma(sm.KQ[l * n + i], Kcol[l], a1);
+#pragma unroll
+                        for (int l = 0; l < m; l++) a2 = fma(sm.K[i * m + l], Quxc[l], a2);
+#pragma unroll
+                        for (int l = 0; l < m; l++) a3 = fma(sm.Qux[i * m + l], Kcol[l], a3);
+                        Scol[i] = ((Qxxc[i] + a1) + a2) + a3;
+                        sm.T[j * n + i] = Scol[i];
+                    }
+                    sm.Sx[j] = Sx_j;
+                }
+                gsync();
+                if (j < n) {
+#pragma unroll
+                    for (int i = 0; i < n; i++) Scol[i] = 0.5 * (Scol[i] + sm.T[i * n + j]);
+                }
+                // dV (replicated)
+                {
+                    double a = 0.0;
+#pragma unroll
+                    for (int l = 0; l < m; l++) a = fma(dk[l], Quv[l], a);
+                    dV0 += a;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int c = 0; c < m; c++) {
+                        double w = 0.0;
+#pragma unroll
+                        for (int l = 0; l < m; l++) w = fma(0.5 * dk[l], Quu[c * m + l], w);
+                        acc = fma(w, dk[c], acc);
+                    }
+                    dV1 += acc;
+                }
+                gsync();
+            }
+            if (!failed) break;
+            if (!store_mode) {
+                store_mode = true;
+                stored_from = N - 1;
+                continue;
+            }
+            reg_update(true);
+        }
+        reg_update(false);
+    }
+};
+
+template <class C, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) ls_bp_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
+    constexpr int GS = ls_group_size<C>();
+    constexpr int GPB = (32 / GS) * WARPS;  // groups per block
+    extern __shared__ __align__(16) unsigned char ls_smem_raw[];
+    BpSmem<C>* smem = reinterpret_cast<BpSmem<C>*>(ls_smem_raw);
+    const unsigned int na = lc.counts[cur];
+    const int g = threadIdx.x / GS, j = threadIdx.x % GS;
+    const int lane = threadIdx.x & 31;
+    const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << (lane - j));
+    const bool al_on = (ctl.mode == 1);
+    for (unsigned int a0 = blockIdx.x * GPB; a0 < na; a0 += gridDim.x * GPB) {
+        const unsigned int a = a0 + g;
+        if (a < na) {
+            const int b = lc.list[cur][a];
+            LsState* st = &lc.st[b];
+            TOiLQROptions io = ctl.o.opts_uncon;
+            BpGroup<C> G(P, smem[g], lc.ws + (size_t)b * lc.ws_stride, j, gmask, al_on, io);
+            G.rho = st->rho;
+            G.drho = st->drho;
+            double dV0, dV1;
+            G.run(dV0, dV1);
+            if (j == 0) {
+                st->rho = G.rho; st->drho = G.drho; st->dV0 = dV0; st->dV1 = dV1;
+                st->winner = -1;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// line search: thread per (problem, step size); G consecutive lanes serve one problem
+// ------------------------------------------------------------------------------------------
+template <class C>
+struct Rollout {
+    // one closed-loop rollout with step size alpha (rollout.jl:2-23) + its cost (objective.jl:40-48 + AL)
+    // WRITE: also store X̄, Ū in place (X <- X̄, U <- Ū) and accumulate the Todorov gradient
+    template <bool WRITE>
+    static __device__ bool run(const DevProblem& P, const TOiLQROptions& io, double* ws, const WsLayout& L, const double* x0,
+                               double alpha, bool al_on, double& Jt, double& grad_sum) {
+        constexpr int n = C::n, m = C::m;
+        const int N = P.N;
+        double xb[n], ub[m];
+#pragma unroll
+        for (int i = 0; i < n; i++) xb[i] = x0[i];
+        bool ok = true;
+        double J = 0.0, Jc = 0.0, gs = 0.0;
+        const double* lam = ws + L.LAM;
+        const double* mu = ws + L.MU;
+        const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
+        for (int k = 0; k < N - 1; k++) {
+            double* Xk = ws + L.X + (size_t)k * n;
+            double* Uk = ws + L.U + (size_t)k * m;
+            const double* Kk = ws + L.KD + (size_t)k * C::KDS;
+            const double* dk = Kk + m * n;
+            double dx[n];
+#pragma unroll
+            for (int i = 0; i < n; i++) dx[i] = xb[i] - Xk[i];
+            double mxg = ninf;
+            bool gnan = false;
+#pragma unroll
+            for (int i = 0; i < m; i++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int c = 0; c < n; c++) acc = fma(Kk[c * m + i], dx[c], acc);
+                const double di = dk[i];
+                ub[i] = (Uk[i] + acc) + alpha * di;
+                if (WRITE) {
+                    const double v = fabs(di) / (fabs(ub[i]) + 1.0);
+                    if (!gnan) {
+                        if (v != v) { mxg = v; gnan = true; }
+                        else mxg = dmax(mxg, v);
+                    }
+                }
+            }
+            if (WRITE) gs += mxg;
+            J += stage_cost<C>(P, xb, ub);
+            if (al_on) Jc += knot_al_cost<C>(P, k, lam, mu, xb, ub);
+            if (WRITE) {
+#pragma unroll
+                for (int i = 0; i < n; i++) Xk[i] = xb[i];
+#pragma unroll
+                for (int i = 0; i < m; i++) Uk[i] = ub[i];
+            }
+            double xn[n];
+            // dyn_eval (augmented model)
+            {
+                double dt = P.dt;
+                if constexpr (C::MT) {
+                    const double h = ub[m - 1];
+                    dt = h * h;
+                }
+                fd_model<C::MODEL, C::INTEG, double>(xn, xb, ub, dt);
+                if constexpr (C::INF) {
+#pragma unroll
+                    for (int i = 0; i < C::n0; i++) xn[i] = xn[i] + ub[C::m0 + i];
+                }
+                if constexpr (C::MT) xn[n - 1] = ub[m - 1];
+            }
+            double mx = 0.0, mu_ = 0.0;
+            bool bad = false;
+#pragma unroll
+            for (int i = 0; i < n; i++) { const double a = fabs(xn[i]); if (a != a) bad = true; mx = dmax(mx, a); }
+#pragma unroll
+            for (int i = 0; i < m; i++) { const double a = fabs(ub[i]); if (a != a) bad = true; mu_ = dmax(mu_, a); }
+            if (bad || !(mx < io.max_state_value && mu_ < io.max_control_value)) ok = false;
+#pragma unroll
+            for (int i = 0; i < n; i++) xb[i] = xn[i];
+        }
+        {
+            double uz[m];
+#pragma unroll
+            for (int i = 0; i < m; i++) uz[i] = 0.0;
+            J += term_cost<C>(P, xb);
+            if (al_on) Jc += knot_al_cost<C>(P, N - 1, lam, mu, xb, uz);
+            if (WRITE) {
+                double* XN = ws + L.X + (size_t)(N - 1) * n;
+#pragma unroll
+                for (int i = 0; i < n; i++) XN[i] = xb[i];
+            }
+        }
+        Jt = al_on ? (J + Jc) : J;
+        grad_sum = gs;
+        return ok;
+    }
+};
+
+// group `grp` of G step sizes: trials grp*G .. grp*G+G-1 (alpha = 2^-trial)
+template <class C, int G>
+__global__ void __launch_bounds__(128) ls_trial_kernel(const DevProblem P, const DevBatch Bt, const DevCtl ctl, const LsCtl lc,
+                                                       const int cur, const int grp) {
+    const int* list = (grp == 0) ? lc.list[cur] : lc.retry[(grp - 1) & 1];
+    const unsigned int na = (grp == 0) ? lc.counts[cur] : lc.counts[2 + ((grp - 1) & 1)];
+    // (the host zeroes counts[2 + (grp & 1)] before launching a group >= 2)
+    const WsLayout L = ws_layout<C>(P.N, P.Ptot, false);
+    const bool al_on = (ctl.mode == 1);
+    const int lane = threadIdx.x & 31;
+    const int t = lane % G;
+    const unsigned int per_block = blockDim.x / G;
+    const unsigned int total = (na + per_block - 1) / per_block * per_block;  // keep warps convergent for the ballot
+    for (unsigned int a0 = blockIdx.x * per_block + threadIdx.x / G; a0 < total; a0 += gridDim.x * per_block) {
+        const bool valid = a0 < na;
+        const int b = valid ? list[a0] : 0;
+        LsState* st = &lc.st[b];
+        TOiLQROptions io = ctl.o.opts_uncon;
+        const int ntrial = io.iterations_linesearch + 1;
+        const int trial = grp * G + t;
+        bool accept = false;
+        double Jt = 0.0, expected = 0.0, z = 0.0;
+        const double alpha = __longlong_as_double((long long)(1023 - trial) << 52);  // 2^-trial
+        if (valid && trial < ntrial) {
+            double* ws = lc.ws + (size_t)b * lc.ws_stride;
+            double x0[C::n];
+#pragma unroll
+            for (int i = 0; i < C::n; i++) x0[i] = (i < C::n0) ? Bt.x0[(size_t)b * C::n0 + i] : 0.0;
+            double gs;
+            const bool ok = Rollout<C>::template run<false>(P, io, ws, L, x0, alpha, al_on, Jt, gs);
+            const double dV0 = st->dV0, dV1 = st->dV1, J_prev = st->J_prev;
+            expected = -alpha * (dV0 + alpha * dV1);
+            z = (expected > 0) ? (J_prev - Jt) / expected : -1.0;
+            const bool cont = (z <= io.line_search_lower_bound || z > io.line_search_upper_bound) && (Jt >= J_prev);
+            accept = ok && !cont;
+        }
+        const unsigned full = __ballot_sync(0xffffffffu, accept);
+        const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - t));
+        const unsigned msk = full & gm;
+        if (valid) {
+            if (msk != 0) {
+                const int wl = __ffs(msk) - 1;  // warp lane of the first accepted trial
+                if (lane == wl) {
+                    st->winner = trial;
+                    st->Jres = Jt; st->exp_res = expected; st->z_res = z;
+                }
+            } else if (t == 0) {
+                // nobody accepted in this group: next group, or a failed line search
+                if ((grp + 1) * G < ntrial) ls_append(lc.retry[grp & 1], &lc.counts[2 + (grp & 1)], b);
+            }
+        }
+    }
+}
+
+// accept the step of every active problem, record the iteration, decide who continues
+template <class C>
+__global__ void __launch_bounds__(64) ls_accept_kernel(const DevProblem P, const DevBatch Bt, const DevCtl ctl, const LsCtl lc, const int cur) {
+    const unsigned int na = lc.counts[cur];
+    const WsLayout L = ws_layout<C>(P.N, P.Ptot, false);
+    const bool al_on = (ctl.mode == 1);
+    const int N = P.N;
+    for (unsigned int a = blockIdx.x * blockDim.x + threadIdx.x; a < na; a += gridDim.x * blockDim.x) {
+        const int b = lc.list[cur][a];
+        LsState* st = &lc.st[b];
+        double* ws = lc.ws + (size_t)b * lc.ws_stride;
+        TOiLQROptions io = ctl.o.opts_uncon;
+        io.cost_tolerance = st->cost_tol;
+        io.gradient_norm_tolerance = st->grad_tol;
+        const int ntrial = io.iterations_linesearch + 1;
+        const double J_prev = st->J_prev;
+        const int w = st->winner;
+        double x0[C::n];
+#pragma unroll
+        for (int i = 0; i < C::n; i++) x0[i] = (i < C::n0) ? Bt.x0[(size_t)b * C::n0 + i] : 0.0;
+        double Jres, gsum = 0.0;
+        bool err;
+        bool copied = false;
+        double rho = st->rho, drho = st->drho;
+        if (w >= 0) {
+            st->ls_count += (unsigned long long)(w + 1);
+            Jres = st->Jres;
+            st->fp_expected = st->exp_res; st->fp_z = st->z_res;
+            st->fp_alpha = __longlong_as_double((long long)(1023 - w) << 52);
+            err = (Jres > J_prev);
+            if (!err && !(Jres > io.max_cost_value)) {
+                double Jt;
+                Rollout<C>::template run<true>(P, io, ws, L, x0, st->fp_alpha, al_on, Jt, gsum);
+                copied = true;
+            }
+        } else {
+            // line search failed (forward_pass.jl:22-37): X̄ <- X, Ū <- U, J recomputed, regularisation bumped
+            st->ls_count += (unsigned long long)ntrial;
+            double J = 0.0, Jc = 0.0;
+            for (int k = 0; k < N; k++) {
+                double x[C::n], u[C::m];
+#pragma unroll
+                for (int i = 0; i < C::n; i++) x[i] = ws[L.X + (size_t)k * C::n + i];
+#pragma unroll
+                for (int i = 0; i < C::m; i++) u[i] = (k < N - 1) ? ws[L.U + (size_t)k * C::m + i] : 0.0;
+                J += (k < N - 1) ? stage_cost<C>(P, x, u) : term_cost<C>(P, x);
+            }
+            if (al_on) {
+                for (int k = 0; k < N; k++) {
+                    double x[C::n], u[C::m];
+#pragma unroll
+                    for (int i = 0; i < C::n; i++) x[i] = ws[L.X + (size_t)k * C::n + i];
+#pragma unroll
+                    for (int i = 0; i < C::m; i++) u[i] = (k < N - 1) ? ws[L.U + (size_t)k * C::m + i] : 0.0;
+                    Jc += knot_al_cost<C>(P, k, ws + L.LAM, ws + L.MU, x, u);
+                }
+            }
+            Jres = al_on ? (J + Jc) : J;
+            st->fp_expected = 0.0; st->fp_z = 0.0; st->fp_alpha = 0.0;
+            const double f = io.bp_reg_increase_factor;
+            drho = dmax(drho * f, f);
+            rho = dmax(rho * drho, io.bp_reg_min);
+            rho += io.bp_reg_fp;
+            err = (Jres > J_prev);
+        }
+        st->rho = rho; st->drho = drho;
+        st->steps += 1;
+        bool inner_done = false;
+        int inner_ok = 1;
+        if (err) {
+            st->status |= TO_STATUS_COST_INCREASED;
+            inner_done = true;
+            inner_ok = 0;
+        } else if (Jres > io.max_cost_value) {
+            st->status |= TO_STATUS_COST_BLOWUP;
+            inner_done = true;
+        } else {
+            if (!copied) {
+                // gradient over the unchanged U and the new d (ilqr_methods.jl:122-129)
+                const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
+                for (int k = 0; k < N - 1; k++) {
+                    const double* d = ws + L.KD + (size_t)k * C::KDS + C::m * C::n;
+                    const double* Uk = ws + L.U + (size_t)k * C::m;
+                    double mx = ninf;
+                    bool isnan_ = false;
+#pragma unroll
+                    for (int i = 0; i < C::m; i++) {
+                        const double v = fabs(d[i]) / (fabs(Uk[i]) + 1.0);
+                        if (!isnan_) {
+                            if (v != v) { mx = v; isnan_ = true; }
+                            else mx = dmax(mx, v);
+                        }
+                    }
+                    gsum += mx;
+                }
+            }
+            const double dJ = fabs(Jres - J_prev);
+            st->J_prev = Jres;
+            // record_inner (ilqr_methods.jl:77-89)
+            const int iterations = st->iterations + 1;
+            st->iterations = iterations;
+            st->last_cost = Jres;
+            st->last_dJ = dJ;
+            double s = gsum;
+            s += 0.0;
+            const double grad = s / (double)N;
+            st->last_grad = grad;
+            int dJ_zero = st->dJ_zero;
+            if (dJ == 0.0) dJ_zero += 1; else dJ_zero = 0;
+            st->dJ_zero = dJ_zero;
+            if (Bt.inner_cap > 0) {
+                int nrec = st->n_inner_rec;
+                if (nrec < Bt.inner_cap) {
+                    TOIterRecord r;
+                    r.cost = Jres; r.dJ = dJ; r.gradient = grad; r.expected = st->fp_expected; r.z = st->fp_z;
+                    r.alpha = st->fp_alpha; r.rho = rho; r.outer = (st->outer_i > 0) ? st->outer_i - 1 : 0; r.iter = iterations;
+                    Bt.inner[(size_t)b * Bt.inner_cap + nrec] = r;
+                    st->n_inner_rec = nrec + 1;
+                } else {
+                    st->status |= TO_STATUS_TRACE_TRUNC;
+                }
+            }
+            // evaluate_convergence (ilqr_methods.jl:139-162)
+            bool conv = false;
+            if (0.0 < dJ && dJ < io.cost_tolerance) conv = true;
+            else if (grad < io.gradient_norm_tolerance) conv = true;
+            else if (iterations >= io.iterations) conv = true;
+            else if (dJ_zero > io.dJ_counter_limit) conv = true;
+            if (conv) {
+                inner_done = true;
+            } else {
+                const int ii = st->inner_i + 1;
+                st->inner_i = ii;
+                if (ii > io.iterations) inner_done = true;
+            }
+        }
+        st->winner = -1;
+        if (inner_done) {
+            st->inner_ok = inner_ok;
+            ls_append(lc.outer_list, &lc.counts[4], b);
+        } else {
+            ls_append(lc.list[cur ^ 1], &lc.counts[cur ^ 1], b);
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// host-side launch table of the lockstep kernels of one configuration
+// ------------------------------------------------------------------------------------------
+constexpr int LS_BP_WARPS = 4;
+constexpr int LS_TRIAL_G = 8;
+
+template <class C> unsigned long long ls_ws_doubles_fn(int N, int Ptot) { return ws_layout<C>(N, Ptot, false).total; }
+
+template <class C> int ls_setup_fn(int sm_count, LsGrids* g) {
+    constexpr int GPB = (32 / ls_group_size<C>()) * LS_BP_WARPS;
+    g->bp_smem = (int)(sizeof(BpSmem<C>) * GPB);
+    g->bp_groups_per_block = GPB;
+    g->trial_group = LS_TRIAL_G;
+    if (cudaFuncSetAttribute(ls_bp_kernel<C, LS_BP_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->bp_smem) != cudaSuccess) return -1;
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_init_kernel<C>, 32, 0);
+    g->init = sm_count * (nb > 0 ? nb : 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_outer_kernel<C>, 32, 0);
+    g->outer = sm_count * (nb > 0 ? nb : 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_jac_kernel<C>, 128, 0);
+    g->jac = sm_count * (nb > 0 ? nb : 1);
+    g->occ_jac = nb;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_bp_kernel<C, LS_BP_WARPS>, 32 * LS_BP_WARPS, g->bp_smem);
+    if (nb < 1) return -2;
+    g->bp = sm_count * nb;
+    g->occ_bp = nb;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_trial_kernel<C, LS_TRIAL_G>, 128, 0);
+    g->trial = sm_count * (nb > 0 ? nb : 1);
+    g->occ_trial = nb;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_accept_kernel<C>, 64, 0);
+    g->accept = sm_count * (nb > 0 ? nb : 1);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+template <class C> void ls_launch_fn(int phase, const LsGrids& g, cudaStream_t st, const DevProblem& P, const DevBatch& B, const DevCtl& c,
+                                     const LsCtl& lc, int cur, int grp) {
+    switch (phase) {
+        case LS_PHASE_INIT: ls_init_kernel<C><<<g.init, 32, 0, st>>>(P, B, c, lc); break;
+        case LS_PHASE_JAC: ls_jac_kernel<C><<<g.jac, 128, 0, st>>>(P, lc, cur); break;
+        case LS_PHASE_BP: ls_bp_kernel<C, LS_BP_WARPS><<<g.bp, 32 * LS_BP_WARPS, g.bp_smem, st>>>(P, c, lc, cur); break;
+        case LS_PHASE_TRIAL: ls_trial_kernel<C, LS_TRIAL_G><<<g.trial, 128, 0, st>>>(P, B, c, lc, cur, grp); break;
+        case LS_PHASE_ACCEPT: ls_accept_kernel<C><<<g.accept, 64, 0, st>>>(P, B, c, lc, cur); break;
+        case LS_PHASE_OUTER: ls_outer_kernel<C><<<g.outer, 32, 0, st>>>(P, B, c, lc, cur); break;
+    }
+}
+
+template <class C> KernelInfo make_info() {
+    KernelInfo k;
+    k.model = C::MODEL; k.integ = C::INTEG; k.inf = C::INF; k.mt = C::MT; k.n = C::n; k.m = C::m;
+    k.smem_bytes = sizeof(Smem<C>);
+    k.ws_doubles = ws_doubles_fn<C>;
+    k.debug_doubles = debug_doubles_fn<C>;
+    k.max_blocks_per_sm = max_blocks_fn<C>;
+    k.launch = launch_fn<C>;
+    k.ls_ws_doubles = ls_ws_doubles_fn<C>;
+    k.ls_setup = ls_setup_fn<C>;
+    k.ls_launch = ls_launch_fn<C>;
+    return k;
+}
+
+}  // namespace tob
