@@ -143,6 +143,9 @@ typedef struct TOALTROOptions {         /* src/solvers/altro/altro_solver.jl:6-6
 #define TO_STATUS_NOT_PD_SQRT    4  /* stage Hessian not PD in cost_expansion_sqrt! (objective.jl:76-93); aborted */
 #define TO_STATUS_MAX_OUTER      8  /* AL iterations exhausted with c_max >= constraint_tolerance */
 #define TO_STATUS_TRACE_TRUNC   16  /* history buffers were too small; records dropped */
+#define TO_STATUS_REG_DIVERGED  32  /* backward pass: the PD test still fails with a non-finite regularisation rho
+                                       (Quu is NaN).  The reference only warns on bp_reg_max (ilqr_methods.jl:169-171)
+                                       and would restart forever (backward_pass.jl:52-63); the solve is aborted instead */
 
 typedef struct TOResult {
     double  J;                 /* last recorded cost (AL: stats[:cost][end]) */

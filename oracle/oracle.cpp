@@ -283,6 +283,7 @@ struct ILQR {  // src/solvers/ilqr/ilqr_solver.jl:93-112
     double last_dJ = 0, last_grad = 0, last_cost = 0;
     // forward-pass log
     double fp_expected = 0, fp_z = 0, fp_alpha = 0;
+    bool rho_diverged = false;
 };
 
 struct AL {  // src/solvers/augmented_lagrangian/augmented_lagrangian_solver.jl:96-110
@@ -640,8 +641,9 @@ static void mul_AB(const double* A, int ra, int ca, const double* Bm, int cb, do
     }
 }
 
-// backward_pass.jl:9-85.  Returns ΔV.
-static void backwardpass(const Spec& S, ILQR& s, double dV[2]) {
+// backward_pass.jl:9-85.  Returns ΔV.  false: the reference's restart loop can no longer make progress
+// (PD test failed with a non-finite rho; the reference would spin forever, see TO_STATUS_REG_DIVERGED).
+static bool backwardpass(const Spec& S, ILQR& s, double dV[2]) {
     const int n = S.n, m = S.m, N = S.N;
     s.Sxx[N - 1] = s.Q[N - 1].xx;
     s.Sx[N - 1] = s.Q[N - 1].x;
@@ -671,6 +673,7 @@ static void backwardpass(const Spec& S, ILQR& s, double dV[2]) {
         for (int i = 0; i < m * m; i++) Quu_reg[i] = Q.uu[i];
         for (int i = 0; i < m; i++) Quu_reg[i * m + i] = Q.uu[i * m + i] + s.rho * 1.0;
         if (!chol_upper(Quu_reg.data(), m, Uc.data())) {
+            if (!std::isfinite(s.rho)) return false;
             reg_update(s, true);
             k = N - 2;
             dV[0] = dV[1] = 0.0;
@@ -711,6 +714,7 @@ static void backwardpass(const Spec& S, ILQR& s, double dV[2]) {
         k--;
     }
     reg_update(s, false);
+    return true;
 }
 
 // cond(A) for the sqrt restart test (backward_pass.jl:129): ratio of extreme singular values.
@@ -795,6 +799,7 @@ static bool backwardpass_sqrt(const Spec& S, ILQR& s, double dV[2]) {
         for (int i = 0; i < m; i++) eye[i * m + i] = sr * 1.0;
         chol_plus(Q.uu.data(), m, eye.data(), m, m, Quu_reg.data());
         if (cond2(Quu_reg.data(), m) > 1e8) {
+            if (!std::isfinite(s.rho)) { s.rho_diverged = true; return false; }
             reg_update(s, true);
             k = N - 2;
             dV[0] = dV[1] = 0.0;
@@ -979,9 +984,9 @@ static bool ilqr_solve(Ctx& c) {
         if (!cost_expansion(S, s, c.al, c.p)) { c.status |= TO_STATUS_NOT_PD_SQRT; return false; }
         double dV[2];
         if (s.o.square_root) {
-            if (!backwardpass_sqrt(S, s, dV)) { c.status |= TO_STATUS_NOT_PD_SQRT; return false; }
+            if (!backwardpass_sqrt(S, s, dV)) { c.status |= s.rho_diverged ? TO_STATUS_REG_DIVERGED : TO_STATUS_NOT_PD_SQRT; return false; }
         } else {
-            backwardpass(S, s, dV);
+            if (!backwardpass(S, s, dV)) { c.status |= TO_STATUS_REG_DIVERGED; return false; }
         }
         bool err = false;
         double J = forwardpass(c, dV, J_prev, err);

@@ -36,6 +36,14 @@ def _quad(B):
     return p, problems.quadrotor_bench_options(), problems.batch_x0("quadrotor", B), None
 
 
+def _quad_regdiv(B):
+    """problems 6324.. of the synthetic quadrotor batch: #6326 makes the reference's backward-pass restart
+    loop diverge (Q1 double accumulation -> NaN Quu -> endless restarts); the engine reports
+    TO_STATUS_REG_DIVERGED instead of hanging."""
+    p = problems.quadrotor()
+    return p, problems.quadrotor_bench_options(), problems.batch_x0("quadrotor", B, offset=6324), None
+
+
 def _quad_ilqr(B):
     p = problems.quadrotor()
     return p, api.iLQRSolverOptions(), problems.batch_x0("quadrotor", B), None
@@ -113,6 +121,7 @@ CASES = {
     "cart_altro": _cart_altro,
     "quad_ilqr": _quad_ilqr,
     "quad_altro": _quad,
+    "quad_regdiv": _quad_regdiv,
     "acrobot_al": _acrobot_al,
     "dp_ilqr": _dp_ilqr,
     "escape_altro": _escape,

@@ -30,6 +30,8 @@ struct Cfg {
     static constexpr int PT = n0 + m0 + (MT_ ? 1 : 0);  // partial directions of the inner model
     static constexpr int NCH = (PT + PC_ - 1) / PC_;
     static constexpr int ZS = n0 * PT;                  // inner Jacobian doubles per knot
+    static constexpr int LDZ = (n + m + 1) & ~1;        // lockstep engine: row-major [A B] per knot, even row length
+    static constexpr int ZA = n * LDZ;
     static constexpr int KDS = m * n + m;               // K and d per knot
     static constexpr int QS = n + m + n * n + m * m + m * n;
 };
@@ -44,7 +46,8 @@ __host__ __device__ inline WsLayout ws_layout(int N, int Ptot, bool candidates =
     unsigned long long o = 0;
     L.X = o;   o += (unsigned long long)N * C::n;
     L.U = o;   o += (unsigned long long)(N - 1) * C::m;
-    L.Z = o;   o += (unsigned long long)(N - 1) * C::ZS;
+    o = (o + 1ull) & ~1ull;  // Z blocks are 16-byte aligned (cp.async 16 B)
+    L.Z = o;   o += (unsigned long long)(N - 1) * (candidates ? C::ZS : C::ZA);
     L.KD = o;  o += (unsigned long long)(N - 1) * C::KDS;
     L.LAM = o; o += Ptot;
     L.MU = o;  o += Ptot;
@@ -732,7 +735,8 @@ struct Solver {
     }
 
     // ---- backward pass (backward_pass.jl:9-85), with the in-place-accumulation restart quirk ----
-    __device__ void backwardpass(double& dV0, double& dV1) {
+    // false: PD test failed with a non-finite rho (TO_STATUS_REG_DIVERGED)
+    __device__ bool backwardpass(double& dV0, double& dV1) {
         constexpr int n = C::n, m = C::m;
         const int N = P.N;
         bool store_mode = false;
@@ -915,9 +919,11 @@ struct Solver {
                 stored_from = N - 1;
                 continue;
             }
+            if (!isfinite(rho)) return false;
             reg_update(true);
         }
         reg_update(false);
+        return true;
     }
 
     // ---- forward pass: all step sizes in parallel (forward_pass.jl:5-85, rollout.jl:2-23) ----
@@ -1115,7 +1121,7 @@ struct Solver {
         for (int i = 1; i <= io.iterations; i++) {
             jacobians();
             double dV0, dV1;
-            backwardpass(dV0, dV1);
+            if (!backwardpass(dV0, dV1)) { status |= TO_STATUS_REG_DIVERGED; return false; }
             if (ctl.debug && b == 0 && ctl.debug_flag && *ctl.debug_flag == 0 && steps == 0) debug_dump(dV0, dV1, J_prev);
             bool err = false;
             const double J = forwardpass(dV0, dV1, J_prev, err);

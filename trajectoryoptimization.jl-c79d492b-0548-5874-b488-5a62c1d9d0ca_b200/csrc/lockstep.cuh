@@ -276,13 +276,35 @@ __global__ void __launch_bounds__(128) ls_jac_kernel(const DevProblem P, const L
             for (int j = 0; j < PC; j++) if (s0 + j == C::n0 + C::m0) dts.p[j] = 1.0;
         }
         fd_model<C::MODEL, C::INTEG, D>(xn, xs, us, dts);
-        double* z = ws + L.Z + (size_t)k * C::ZS;
+        // row-major [A_k B_k] of the AUGMENTED model, rows of C::LDZ doubles
+        // (add_slack_controls: src/model.jl:761-779; add_min_time_controls: minimum_time.jl:85-104)
+        double* ab = ws + L.Z + (size_t)k * C::ZA;
+        double h2 = 0.0;
+        if constexpr (C::MT) h2 = 2.0 * uk[C::m - 1];
 #pragma unroll
         for (int j = 0; j < PC; j++) {
-            if (s0 + j < C::PT) {
+            const int c = s0 + j;
+            if (c < C::PT) {
+                const int col = (c < C::n0) ? c : ((c < C::n0 + C::m0) ? C::n + (c - C::n0) : C::n + C::m - 1);
+                const bool is_dt = (C::MT && c == C::n0 + C::m0);
 #pragma unroll
-                for (int i = 0; i < C::n0; i++) z[(s0 + j) * C::n0 + i] = xn[i].p[j];
+                for (int i = 0; i < C::n0; i++) ab[i * C::LDZ + col] = is_dt ? xn[i].p[j] * h2 : xn[i].p[j];
             }
+        }
+        if (ch == 0 && (C::INF || C::MT)) {
+            // the constant entries of the augmented Jacobian
+            for (int i = 0; i < C::n; i++)
+                for (int jj = 0; jj < C::n + C::m; jj++) {
+                    const bool dyn = (i < C::n0) && (jj < C::n0 || (jj >= C::n && jj < C::n + C::m0) || (C::MT && jj == C::n + C::m - 1));
+                    if (dyn) continue;
+                    double v = 0.0;
+                    if (jj >= C::n) {
+                        const int bcol = jj - C::n;
+                        if (C::INF && bcol >= C::m0 && bcol < C::m0 + C::n0) v = (i == bcol - C::m0) ? 1.0 : 0.0;
+                        else if (C::MT && bcol == C::m - 1 && i == C::n - 1) v = 1.0;
+                    }
+                    ab[i * C::LDZ + jj] = v;
+                }
         }
     }
 }
@@ -291,18 +313,42 @@ __global__ void __launch_bounds__(128) ls_jac_kernel(const DevProblem P, const L
 // backward pass: GS lanes per problem, lane j owns column j
 // ------------------------------------------------------------------------------------------
 template <class C>
-struct BpSmem {
-    double A[C::n * C::n], B[C::n * C::m];
-    double T[C::n * C::n], Tu[C::m * C::n];
-    double K[C::m * C::n], Qux[C::m * C::n], Quu[C::m * C::m], KQ[C::n * C::m];
-    double Sx[C::n], Qu[C::m], d[C::m], xk[C::n], uk[C::m], vQx[C::nq], vQu[C::mq];
+struct alignas(16) BpSmem {
+    static constexpr int n = C::n, m = C::m;
+    static constexpr int LDn = (n + 1) & ~1;   // even leading dimension: rows start 16-byte aligned
+    static constexpr int LDm = (m + 1) & ~1;
+    static constexpr int LDZ = C::LDZ;
+    static constexpr int XU = (n + m + 1) & ~1;
+    static constexpr int LAMCAP = 32;          // multipliers / penalties of one knot staged by the prefetch (larger sets read global)
+    // double-buffered per-knot inputs, filled by cp.async one knot ahead
+    double AB[2][n * LDZ];   // row l = [A(l,0..n-1) B(l,0..m-1)]
+    double xu[2][XU];        // [x_k ; u_k]
+    double lam[2][LAMCAP], mu[2][LAMCAP];
+    // products streamed by the other lanes of the group (all "left operand, contiguous in the output row index")
+    double T[n * LDn];       // T(i,l) at [l*LDn+i]; later the unsymmetrised S.xx
+    double Tu[n * LDm];      // Tu(i,l) at [l*LDm+i]
+    double KT[m * LDn];      // K(l,i)   at [l*LDn+i]
+    double QuxT[m * LDn];    // Qux(l,i) at [l*LDn+i]
+    double KQ[m * LDn];      // KQ(i,l)  at [l*LDn+i]
+    double Quu[m * m], Sx[n], Qu[m], d[m], vQx[C::nq], vQu[C::mq], xN[n];
 };
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 template <class C>
 struct BpGroup {
     static constexpr int n = C::n, m = C::m, n0 = C::n0, m0 = C::m0, nq = C::nq, mq = C::mq;
     static constexpr int GS = ls_group_size<C>();
     static constexpr int DL = (n < GS) ? n : 0;  // lane that solves for the feed-forward term d
+    static constexpr int LDn = BpSmem<C>::LDn, LDm = BpSmem<C>::LDm, LDZ = BpSmem<C>::LDZ, LAMCAP = BpSmem<C>::LAMCAP;
     const DevProblem& P;
     BpSmem<C>& sm;
     double* ws;
@@ -313,15 +359,13 @@ struct BpGroup {
     TOiLQROptions io;
     double rho, drho;
     // register-resident columns
-    double Scol[n], Acol[n], Bcol[n], Qxxc[n], Quxc[m], Quuc[m], Kcol[m];
+    double Scol[n], Acol[n], Qxxc[n], Quxc[m], Quuc[m], Kcol[m];
     double Qx_j, Qu_j, Sx_j;
 
     __device__ BpGroup(const DevProblem& P_, BpSmem<C>& s_, double* ws_, int j_, unsigned gmask_, bool al_on_, const TOiLQROptions& io_)
         : P(P_), sm(s_), ws(ws_), L(ws_layout<C>(P_.N, P_.Ptot, false)), j(j_), gmask(gmask_), al_on(al_on_), io(io_) {}
 
     __device__ void gsync() { __syncwarp(gmask); }
-    __device__ const double* X(int k) { return ws + L.X + (size_t)k * n; }
-    __device__ const double* U(int k) { return ws + L.U + (size_t)k * m; }
 
     __device__ void reg_update(bool increase) {  // ilqr_methods.jl:164-176
         const double f = io.bp_reg_increase_factor;
@@ -334,50 +378,35 @@ struct BpGroup {
         }
     }
 
-    // columns j of A_k, B_k of the augmented model -> registers + shared memory
-    __device__ void load_AB(int k) {
-        const double* z = ws + L.Z + (size_t)k * C::ZS;
-        if (j < n) {
-#pragma unroll
-            for (int i = 0; i < n; i++) {
-                const double v = (i < n0 && j < n0) ? z[j * n0 + i] : 0.0;
-                Acol[i] = v;
-                sm.A[j * n + i] = v;
-            }
-        }
-        if (j < m) {
-            double h2 = 0.0;
-            if constexpr (C::MT) h2 = 2.0 * U(k)[m - 1];
-#pragma unroll
-            for (int i = 0; i < n; i++) {
-                double v = 0.0;
-                if (j < m0) {
-                    if (i < n0) v = z[(n0 + j) * n0 + i];
-                } else if (C::INF && j < m0 + n0) {
-                    v = (i == j - m0) ? 1.0 : 0.0;
-                } else if (C::MT && j == m - 1) {
-                    if (i < n0) v = z[(n0 + m0) * n0 + i] * h2;
-                    else if (i == n - 1) v = 1.0;
+    // asynchronous copy of knot k's inputs ([A B], x, u, lambda, mu) into buffer `buf`
+    __device__ void prefetch(int k, int buf) {
+        const double* ab = ws + L.Z + (size_t)k * C::ZA;  // 16-byte aligned, C::ZA even
+        for (int e = 2 * j; e < C::ZA; e += 2 * GS) cp_async16(&sm.AB[buf][e], ab + e);
+        const double* xk = ws + L.X + (size_t)k * n;
+        const double* uk = ws + L.U + (size_t)k * m;
+        for (int e = j; e < n + m; e += GS) cp_async8(&sm.xu[buf][e], (e < n) ? (xk + e) : (uk + (e - n)));
+        if (al_on) {
+            const int rc = P.knot_row_count[k], lo = P.knot_lam_off[k];
+            if (rc <= LAMCAP) {
+                for (int e = j; e < rc; e += GS) {
+                    cp_async8(&sm.lam[buf][e], ws + L.LAM + lo + e);
+                    cp_async8(&sm.mu[buf][e], ws + L.MU + lo + e);
                 }
-                Bcol[i] = v;
-                sm.B[j * n + i] = v;
             }
         }
     }
 
     // cost expansion of knot k (+ AL terms), column j -> registers
     // (src/cost.jl:183-198, minimum_time.jl:161-204, augmented_lagrangian_methods.jl:186-229)
-    __device__ void expansion(int k) {
+    // `xs`: the knot's [x;u] in shared memory (u ignored at the terminal knot); `lams`/`mus`: its multipliers / penalties
+    __device__ void expansion(int k, const double* xs, const double* lams, const double* mus) {
         const int N = P.N;
         const bool term = (k == N - 1);
-        if (j < n) sm.xk[j] = X(k)[j];
-        if (j < m) sm.uk[j] = term ? 0.0 : U(k)[j];
-        gsync();
         double x[n], u[m];
 #pragma unroll
-        for (int i = 0; i < n; i++) x[i] = sm.xk[i];
+        for (int i = 0; i < n; i++) x[i] = xs[i];
 #pragma unroll
-        for (int i = 0; i < m; i++) u[i] = sm.uk[i];
+        for (int i = 0; i < m; i++) u[i] = term ? 0.0 : xs[n + i];
         const double* Qm = term ? P.Qf : P.Q;
         const double* qv = term ? P.qf : P.q;
         const bool qd = term ? P.qf_diag : P.q_diag;
@@ -459,10 +488,10 @@ struct BpGroup {
             Qu_j = v;
         }
         if (!al_on) return;
-        const int rb = P.knot_row_begin[k], rc = P.knot_row_count[k], lo = P.knot_lam_off[k];
+        const int rb = P.knot_row_begin[k], rc = P.knot_row_count[k];
         if (rc == 0) return;
-        const double* lamk = ws + L.LAM + lo;
-        const double* muk = ws + L.MU + lo;
+        const double* lamk = lams;
+        const double* muk = mus;
         double axx[n], aux_[m], auu[m], ax = 0.0, au = 0.0;
 #pragma unroll
         for (int i = 0; i < n; i++) axx[i] = 0.0;
@@ -678,13 +707,21 @@ struct BpGroup {
     }
 
     // the whole backward pass of one problem, including regularisation restarts
-    __device__ void run(double& dV0, double& dV1) {
+    __device__ bool run(double& dV0, double& dV1) {
         const int N = P.N;
         bool store_mode = false;
         int stored_from = N - 1;
         for (;;) {
+            cp_async_wait_all();
+            gsync();
+            prefetch(N - 2, (N - 2) & 1);
             // terminal cost-to-go: S = Qxx_N, Sx = Qx_N
-            expansion(N - 1);
+            if (j < n) sm.xN[j] = ws[L.X + (size_t)(N - 1) * n + j];
+            gsync();
+            {
+                const int lo = P.knot_lam_off[N - 1];
+                expansion(N - 1, sm.xN, ws + L.LAM + lo, ws + L.MU + lo);
+            }
             if (j < n) {
 #pragma unroll
                 for (int i = 0; i < n; i++) Scol[i] = Qxxc[i];
@@ -693,78 +730,92 @@ struct BpGroup {
             dV0 = 0.0;
             dV1 = 0.0;
             bool failed = false;
-            gsync();
             for (int k = N - 2; k >= 0; k--) {
-                load_AB(k);
+                const int buf = k & 1;
+                cp_async_wait_all();
+                gsync();  // knot k's inputs have landed; every lane is done with knot k+1
+                if (k > 0) prefetch(k - 1, buf ^ 1);
+                const double* AB = sm.AB[buf];
+                if (j < n) {
+#pragma unroll
+                    for (int l = 0; l < n; l++) Acol[l] = AB[l * LDZ + j];
+                }
                 if (store_mode && k >= stored_from) {
                     q_load(k);
-                    gsync();
                 } else {
-                    expansion(k);
-                    gsync();
+                    const int rc = P.knot_row_count[k], lo = P.knot_lam_off[k];
+                    const bool staged = (rc <= LAMCAP);
+                    expansion(k, sm.xu[buf], staged ? sm.lam[buf] : ws + L.LAM + lo, staged ? sm.mu[buf] : ws + L.MU + lo);
                 }
-                // Qx += A'Sx ; Qu += B'Sx
+                // Qx += A'Sx ; Qu += B'Sx ; T = A'S (column j) ; Tu = B'S (column j)
                 if (j < n) {
                     double acc = 0.0;
 #pragma unroll
                     for (int l = 0; l < n; l++) acc = fma(Acol[l], sm.Sx[l], acc);
                     Qx_j += acc;
+                    double t[n], tu[m];
+#pragma unroll
+                    for (int i = 0; i < n; i++) t[i] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < m; i++) tu[i] = 0.0;
+#pragma unroll
+                    for (int l = 0; l < n; l++) {
+                        const double s_l = Scol[l];
+#pragma unroll
+                        for (int i = 0; i < n; i++) t[i] = fma(AB[l * LDZ + i], s_l, t[i]);
+#pragma unroll
+                        for (int i = 0; i < m; i++) tu[i] = fma(AB[l * LDZ + n + i], s_l, tu[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < n; i++) sm.T[j * LDn + i] = t[i];
+#pragma unroll
+                    for (int i = 0; i < m; i++) sm.Tu[j * LDm + i] = tu[i];
                 }
                 if (j < m) {
                     double acc = 0.0;
 #pragma unroll
-                    for (int l = 0; l < n; l++) acc = fma(Bcol[l], sm.Sx[l], acc);
+                    for (int l = 0; l < n; l++) acc = fma(AB[l * LDZ + n + j], sm.Sx[l], acc);
                     Qu_j += acc;
-                }
-                // T = A'S (column j), Tu = B'S (column j)
-                if (j < n) {
-#pragma unroll
-                    for (int i = 0; i < n; i++) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int l = 0; l < n; l++) acc = fma(sm.A[i * n + l], Scol[l], acc);
-                        sm.T[j * n + i] = acc;
-                    }
-#pragma unroll
-                    for (int i = 0; i < m; i++) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int l = 0; l < n; l++) acc = fma(sm.B[i * n + l], Scol[l], acc);
-                        sm.Tu[j * m + i] = acc;
-                    }
                 }
                 gsync();
                 // Qxx += T*A ; Qux += Tu*A ; Quu += Tu*B
                 if (j < n) {
+                    double a1[n], a2[m];
 #pragma unroll
-                    for (int i = 0; i < n; i++) {
-                        double acc = 0.0;
+                    for (int i = 0; i < n; i++) a1[i] = 0.0;
 #pragma unroll
-                        for (int l = 0; l < n; l++) acc = fma(sm.T[l * n + i], Acol[l], acc);
-                        Qxxc[i] += acc;
+                    for (int i = 0; i < m; i++) a2[i] = 0.0;
+#pragma unroll
+                    for (int l = 0; l < n; l++) {
+                        const double a_l = Acol[l];
+#pragma unroll
+                        for (int i = 0; i < n; i++) a1[i] = fma(sm.T[l * LDn + i], a_l, a1[i]);
+#pragma unroll
+                        for (int i = 0; i < m; i++) a2[i] = fma(sm.Tu[l * LDm + i], a_l, a2[i]);
                     }
 #pragma unroll
-                    for (int i = 0; i < m; i++) {
-                        double acc = 0.0;
+                    for (int i = 0; i < n; i++) Qxxc[i] += a1[i];
 #pragma unroll
-                        for (int l = 0; l < n; l++) acc = fma(sm.Tu[l * m + i], Acol[l], acc);
-                        Quxc[i] += acc;
-                    }
+                    for (int i = 0; i < m; i++) Quxc[i] += a2[i];
                 }
                 if (j < m) {
+                    double a3[m];
 #pragma unroll
-                    for (int i = 0; i < m; i++) {
-                        double acc = 0.0;
+                    for (int i = 0; i < m; i++) a3[i] = 0.0;
 #pragma unroll
-                        for (int l = 0; l < n; l++) acc = fma(sm.Tu[l * m + i], Bcol[l], acc);
-                        Quuc[i] += acc;
+                    for (int l = 0; l < n; l++) {
+                        const double b_l = AB[l * LDZ + n + j];
+#pragma unroll
+                        for (int i = 0; i < m; i++) a3[i] = fma(sm.Tu[l * LDm + i], b_l, a3[i]);
                     }
+#pragma unroll
+                    for (int i = 0; i < m; i++) Quuc[i] += a3[i];
                 }
                 if (store_mode) {
                     q_store(k);
                     if (k < stored_from) stored_from = k;
                 }
-                // publish Quu, Qux, Qu
+                // publish Quu, Qu, Qux'
                 if (j < m) {
 #pragma unroll
                     for (int i = 0; i < m; i++) sm.Quu[j * m + i] = Quuc[i];
@@ -772,7 +823,7 @@ struct BpGroup {
                 }
                 if (j < n) {
 #pragma unroll
-                    for (int i = 0; i < m; i++) sm.Qux[j * m + i] = Quxc[i];
+                    for (int l = 0; l < m; l++) sm.QuxT[l * LDn + j] = Quxc[l];
                 }
                 gsync();
                 // Quu_reg = Quu + rho*I, replicated per lane
@@ -792,7 +843,7 @@ struct BpGroup {
 #pragma unroll
                     for (int i = 0; i < m; i++) {
                         Kcol[i] = -1.0 * rhs[i];
-                        sm.K[j * m + i] = Kcol[i];
+                        sm.KT[i * LDn + j] = Kcol[i];
                     }
                 }
                 if (j == DL) {
@@ -802,6 +853,18 @@ struct BpGroup {
                     lu_solve(f, rhs);
 #pragma unroll
                     for (int i = 0; i < m; i++) sm.d[i] = -1.0 * rhs[i];
+                }
+                // KQ = K'Quu (row j)
+                double KQr[m];
+                if (j < n) {
+#pragma unroll
+                    for (int c = 0; c < m; c++) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < m; l++) acc = fma(Kcol[l], Quu[c * m + l], acc);
+                        KQr[c] = acc;
+                        sm.KQ[c * LDn + j] = acc;
+                    }
                 }
                 gsync();
                 double dk[m], Quv[m];
@@ -818,17 +881,8 @@ struct BpGroup {
                         for (int i = 0; i < m; i++) kd[m * n + i] = dk[i];
                     }
                 }
-                // KQ = K'Quu (row j), S.x
                 if (j < n) {
-                    double KQr[m];
-#pragma unroll
-                    for (int c = 0; c < m; c++) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int l = 0; l < m; l++) acc = fma(Kcol[l], Quu[c * m + l], acc);
-                        KQr[c] = acc;
-                        sm.KQ[c * n + j] = acc;
-                    }
+                    // S.x = Qx + KQ d + K'Qu + Qux'd
                     double a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
                     for (int l = 0; l < m; l++) a1 = fma(KQr[l], dk[l], a1);
@@ -837,28 +891,31 @@ struct BpGroup {
 #pragma unroll
                     for (int l = 0; l < m; l++) a3 = fma(Quxc[l], dk[l], a3);
                     Sx_j = ((Qx_j + a1) + a2) + a3;
-                }
-                gsync();
-                // unsymmetrised S.xx, column j -> T
-                if (j < n) {
+                    // unsymmetrised S.xx, column j: Qxx + KQ*K + K'Qux + Qux'K
+                    double b1[n], b2[n], b3[n];
+#pragma unroll
+                    for (int i = 0; i < n; i++) { b1[i] = 0.0; b2[i] = 0.0; b3[i] = 0.0; }
+#pragma unroll
+                    for (int l = 0; l < m; l++) {
+                        const double k_l = Kcol[l], q_l = Quxc[l];
+#pragma unroll
+                        for (int i = 0; i < n; i++) {
+                            b1[i] = fma(sm.KQ[l * LDn + i], k_l, b1[i]);
+                            b2[i] = fma(sm.KT[l * LDn + i], q_l, b2[i]);
+                            b3[i] = fma(sm.QuxT[l * LDn + i], k_l, b3[i]);
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < n; i++) {
-                        double a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-                        for (int l = 0; l < m; l++) a1 = fma(sm.KQ[l * n + i], Kcol[l], a1);
-#pragma unroll
-                        for (int l = 0; l < m; l++) a2 = fma(sm.K[i * m + l], Quxc[l], a2);
-#pragma unroll
-                        for (int l = 0; l < m; l++) a3 = fma(sm.Qux[i * m + l], Kcol[l], a3);
-                        Scol[i] = ((Qxxc[i] + a1) + a2) + a3;
-                        sm.T[j * n + i] = Scol[i];
+                        Scol[i] = ((Qxxc[i] + b1[i]) + b2[i]) + b3[i];
+                        sm.T[j * LDn + i] = Scol[i];
                     }
                     sm.Sx[j] = Sx_j;
                 }
                 gsync();
                 if (j < n) {
 #pragma unroll
-                    for (int i = 0; i < n; i++) Scol[i] = 0.5 * (Scol[i] + sm.T[i * n + j]);
+                    for (int i = 0; i < n; i++) Scol[i] = 0.5 * (Scol[i] + sm.T[i * LDn + j]);
                 }
                 // dV (replicated)
                 {
@@ -876,7 +933,6 @@ struct BpGroup {
                     }
                     dV1 += acc;
                 }
-                gsync();
             }
             if (!failed) break;
             if (!store_mode) {
@@ -884,9 +940,15 @@ struct BpGroup {
                 stored_from = N - 1;
                 continue;
             }
+            if (!isfinite(rho)) {
+                cp_async_wait_all();
+                return false;
+            }
             reg_update(true);
         }
+        cp_async_wait_all();
         reg_update(false);
+        return true;
     }
 };
 
@@ -911,10 +973,11 @@ __global__ void __launch_bounds__(32 * WARPS) ls_bp_kernel(const DevProblem P, c
             G.rho = st->rho;
             G.drho = st->drho;
             double dV0, dV1;
-            G.run(dV0, dV1);
+            const bool ok = G.run(dV0, dV1);
             if (j == 0) {
                 st->rho = G.rho; st->drho = G.drho; st->dV0 = dV0; st->dV1 = dV1;
                 st->winner = -1;
+                st->bp_fail = ok ? 0 : 1;
             }
         }
     }
@@ -1040,7 +1103,8 @@ __global__ void __launch_bounds__(128) ls_trial_kernel(const DevProblem P, const
         bool accept = false;
         double Jt = 0.0, expected = 0.0, z = 0.0;
         const double alpha = __longlong_as_double((long long)(1023 - trial) << 52);  // 2^-trial
-        if (valid && trial < ntrial) {
+        const bool bp_fail = valid && (st->bp_fail != 0);  // backward pass aborted: no line search for this problem
+        if (valid && !bp_fail && trial < ntrial) {
             double* ws = lc.ws + (size_t)b * lc.ws_stride;
             double x0[C::n];
 #pragma unroll
@@ -1056,7 +1120,7 @@ __global__ void __launch_bounds__(128) ls_trial_kernel(const DevProblem P, const
         const unsigned full = __ballot_sync(0xffffffffu, accept);
         const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - t));
         const unsigned msk = full & gm;
-        if (valid) {
+        if (valid && !bp_fail) {
             if (msk != 0) {
                 const int wl = __ffs(msk) - 1;  // warp lane of the first accepted trial
                 if (lane == wl) {
@@ -1095,6 +1159,15 @@ __global__ void __launch_bounds__(64) ls_accept_kernel(const DevProblem P, const
         bool err;
         bool copied = false;
         double rho = st->rho, drho = st->drho;
+        if (st->bp_fail) {
+            // the reference would restart its backward pass forever (TO_STATUS_REG_DIVERGED): abort this solve
+            st->bp_fail = 0;
+            st->status |= TO_STATUS_REG_DIVERGED;
+            st->winner = -1;
+            st->inner_ok = 0;
+            ls_append(lc.outer_list, &lc.counts[4], b);
+            continue;
+        }
         if (w >= 0) {
             st->ls_count += (unsigned long long)(w + 1);
             Jres = st->Jres;
