@@ -321,13 +321,48 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
     const int ngroups = (ntrial + G - 1) / G;
     // worst case number of ticks: every AL iteration runs every allowed inner step
     const long long max_ticks = (long long)std::max(1, c.o.iterations) * (long long)std::max(1, c.o.opts_uncon.iterations) + 8;
+    // tail mode: with few live problems a tick is latency-bound, so every step size is tried in ONE launch
+    // (a warp per problem) instead of G at a time
+    unsigned int tail_threshold = (unsigned int)s->sm_count * 8u;
+    if (const char* env = getenv("TRAJOPT_B200_TAIL_THRESHOLD")) tail_threshold = (unsigned int)atoi(env);  // 0 disables tail mode
+    unsigned int known_active = (unsigned int)s->B;  // upper bound (the list only shrinks), refreshed LAG ticks late
+    // diagnostics: TRAJOPT_B200_TICK_LOG=<file> records one event per tick and writes "tick ms active" lines
+    const char* tick_log = getenv("TRAJOPT_B200_TICK_LOG");
+    std::vector<cudaEvent_t> tick_ev;
+    std::vector<unsigned int> tick_active;
+    auto dump_ticks = [&]() {
+        if (!tick_log || tick_ev.size() < 2) return;
+        cudaStreamSynchronize(st);
+        FILE* f = fopen(tick_log, "a");
+        if (f) {
+            fprintf(f, "# solve B=%d ticks=%zu\n", s->B, tick_ev.size() - 1);
+            for (size_t i = 1; i < tick_ev.size(); i++) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, tick_ev[i - 1], tick_ev[i]);
+                fprintf(f, "%zu %.4f %u\n", i - 1, ms, i - 1 < tick_active.size() ? tick_active[i - 1] : 0u);
+            }
+            fclose(f);
+        }
+        for (auto e : tick_ev) cudaEventDestroy(e);
+    };
+    if (tick_log) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tick_ev.push_back(e);
+    }
     for (long long t = 0; t < max_ticks; t++) {
         const int cur = (int)(t & 1);
         v.ki->ls_launch(LS_PHASE_JAC, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
         v.ki->ls_launch(LS_PHASE_BP, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
-        for (int g = 0; g < ngroups; g++) {
-            if (g >= 2) CK_RET(s, cudaMemsetAsync(v.lc.counts + 2 + (g & 1), 0, sizeof(unsigned int), st));
-            v.ki->ls_launch(LS_PHASE_TRIAL, v.grids, st, v.P, Bt, c, v.lc, cur, g);
+        if (known_active <= tail_threshold && ntrial <= 32) {
+            v.ki->ls_launch(LS_PHASE_TRIAL_ALL, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+            s->launches -= ngroups - 1;
+        } else {
+            for (int g = 0; g < ngroups; g++) {
+                if (g >= 2) CK_RET(s, cudaMemsetAsync(v.lc.counts + 2 + (g & 1), 0, sizeof(unsigned int), st));
+                v.ki->ls_launch(LS_PHASE_TRIAL, v.grids, st, v.P, Bt, c, v.lc, cur, g);
+            }
         }
         v.ki->ls_launch(LS_PHASE_ACCEPT, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
         v.ki->ls_launch(LS_PHASE_OUTER, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
@@ -337,12 +372,21 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
         const int slot = (int)(t % RING);
         CK_RET(s, cudaMemcpyAsync(&s->h_counts[slot], v.lc.counts + (cur ^ 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         CK_RET(s, cudaEventRecord(s->ring_ev[slot], st));
+        if (tick_log) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, st);
+            tick_ev.push_back(e);
+        }
         if (t >= LAG) {
             const int old = (int)((t - LAG) % RING);
             CK_RET(s, cudaEventSynchronize(s->ring_ev[old]));
-            if (s->h_counts[old] == 0) return 0;
+            known_active = s->h_counts[old];
+            if (tick_log) tick_active.push_back(known_active);
+            if (known_active == 0) { dump_ticks(); return 0; }
         }
     }
+    dump_ticks();
     return 0;
 }
 

@@ -234,21 +234,21 @@ __global__ void __launch_bounds__(32) ls_outer_kernel(const DevProblem P, const 
 }
 
 // ---- Jacobians: thread per (problem, knot, chunk of partial directions) -----------------------
-template <class C>
+template <class C, int PC>
 __global__ void __launch_bounds__(128) ls_jac_kernel(const DevProblem P, const LsCtl lc, const int cur) {
-    constexpr int PC = C::PC;
+    constexpr int NCH = (C::PT + PC - 1) / PC;
     typedef Dual<PC> D;
     const unsigned int na = lc.counts[cur];
     if (blockIdx.x == 0 && threadIdx.x == 0) { lc.counts[cur ^ 1] = 0; lc.counts[2] = 0; lc.counts[3] = 0; lc.counts[4] = 0; }
     const int N = P.N;
-    const unsigned int per = (unsigned int)(N - 1) * C::NCH;
+    const unsigned int per = (unsigned int)(N - 1) * NCH;
     const unsigned long long items = (unsigned long long)na * per;
     const WsLayout L = ws_layout<C>(N, P.Ptot, false);
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < items; t += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned int a = (unsigned int)(t / per), it = (unsigned int)(t - (unsigned long long)a * per);
         const int b = lc.list[cur][a];
         double* ws = lc.ws + (size_t)b * lc.ws_stride;
-        const int k = it / C::NCH, ch = it - k * C::NCH;
+        const int k = it / NCH, ch = it - k * NCH;
         const int s0 = ch * PC;
         D xs[C::n0], us[C::m0], dts, xn[C::n0];
         const double* xk = ws + L.X + (size_t)k * C::n;
@@ -319,7 +319,7 @@ struct alignas(16) BpSmem {
     static constexpr int LDm = (m + 1) & ~1;
     static constexpr int LDZ = C::LDZ;
     static constexpr int XU = (n + m + 1) & ~1;
-    static constexpr int LAMCAP = 32;          // multipliers / penalties of one knot staged by the prefetch (larger sets read global)
+    static constexpr int LAMCAP = 16;          // multipliers / penalties of one knot staged by the prefetch (larger sets read global)
     // double-buffered per-knot inputs, filled by cp.async one knot ahead
     double AB[2][n * LDZ];   // row l = [A(l,0..n-1) B(l,0..m-1)]
     double xu[2][XU];        // [x_k ; u_k]
@@ -359,7 +359,7 @@ struct BpGroup {
     TOiLQROptions io;
     double rho, drho;
     // register-resident columns
-    double Scol[n], Acol[n], Qxxc[n], Quxc[m], Quuc[m], Kcol[m];
+    double Scol[n], Qxxc[n], Quxc[m], Quuc[m], Kcol[m];
     double Qx_j, Qu_j, Sx_j;
 
     __device__ BpGroup(const DevProblem& P_, BpSmem<C>& s_, double* ws_, int j_, unsigned gmask_, bool al_on_, const TOiLQROptions& io_)
@@ -396,77 +396,187 @@ struct BpGroup {
         }
     }
 
+    // constraint row value / Jacobian entry with z̄ = [x̄;ū] read from shared memory (same expressions as
+    // row_value / row_jac in engine.cuh)
+    __device__ static double row_value_s(const DevRow& r, const double* zs) {
+        switch (r.kind) {
+            case DR_LIN: {
+                const double z = zs[r.col];
+                return (r.sign > 0) ? (z - r.a) : (r.a - z);
+            }
+            case DR_CIRCLE: {
+                const double dx = zs[0] - r.a, dy = zs[1] - r.b;
+                return -(((dx * dx) + (dy * dy)) - (r.r * r.r));
+            }
+            case DR_SPHERE: {
+                if constexpr (n >= 3) {
+                    const double dx = zs[0] - r.a, dy = zs[1] - r.b, dz = zs[2] - r.c;
+                    return -((((dx * dx) + (dy * dy)) + (dz * dz)) - (r.r * r.r));
+                } else {
+                    return 0.0;
+                }
+            }
+            default: return zs[n + m - 1] - zs[n - 1];
+        }
+    }
+    __device__ static double row_jac_s(const DevRow& r, const double* zs, int col) {
+        switch (r.kind) {
+            case DR_LIN: return (col == r.col) ? ((r.sign > 0) ? 1.0 : -1.0) : 0.0;
+            case DR_CIRCLE: return (col == 0) ? -(2.0 * (zs[0] - r.a)) : ((col == 1) ? -(2.0 * (zs[1] - r.b)) : 0.0);
+            case DR_SPHERE:
+                if constexpr (n >= 3)
+                    return (col == 0) ? -(2.0 * (zs[0] - r.a)) : ((col == 1) ? -(2.0 * (zs[1] - r.b)) : ((col == 2) ? -(2.0 * (zs[2] - r.c)) : 0.0));
+                else
+                    return 0.0;
+            default: return (col == n + m - 1) ? 1.0 : ((col == n - 1) ? -1.0 : 0.0);
+        }
+    }
+
     // cost expansion of knot k (+ AL terms), column j -> registers
     // (src/cost.jl:183-198, minimum_time.jl:161-204, augmented_lagrangian_methods.jl:186-229)
-    // `xs`: the knot's [x;u] in shared memory (u ignored at the terminal knot); `lams`/`mus`: its multipliers / penalties
+    // `xs`: the knot's [x;u] in shared memory (u ignored at the terminal knot); `lams`/`mus`: its multipliers / penalties.
+    // The AL sums are accumulated first (from zero, in row order) and the cost blocks added to them afterwards,
+    // which is the same value as adding the finished sums to the blocks.  Bound / goal / slack rows (one ±1 entry)
+    // only touch the diagonal element and the gradient entry of the lane that owns their column.
     __device__ void expansion(int k, const double* xs, const double* lams, const double* mus) {
         const int N = P.N;
         const bool term = (k == N - 1);
-        double x[n], u[m];
+        const int rb = P.knot_row_begin[k], rc = al_on ? P.knot_row_count[k] : 0;
+        const bool has_al = rc > 0;
+        double dxx = 0.0, duu = 0.0, ax = 0.0, au = 0.0;
 #pragma unroll
-        for (int i = 0; i < n; i++) x[i] = xs[i];
+        for (int i = 0; i < n; i++) Qxxc[i] = 0.0;
 #pragma unroll
-        for (int i = 0; i < m; i++) u[i] = term ? 0.0 : xs[n + i];
+        for (int i = 0; i < m; i++) { Quxc[i] = 0.0; Quuc[i] = 0.0; }
+        for (int r_ = 0; r_ < rc; r_++) {
+            const DevRow r = P.rows[rb + r_];
+            if (r.kind == DR_LIN) {
+                const int col = r.col;
+                const bool ownx = (j < n) && (col == j);
+                const bool ownu = !term && (j < m) && (col == n + j);
+                if (ownx || ownu) {
+                    const double z = xs[col];
+                    const double c = (r.sign > 0) ? (z - r.a) : (r.a - z);
+                    const double lam_r = lams[r_];
+                    const bool act = r.eq ? true : ((c >= 0.0) || (lam_r > 0.0));
+                    const double im = act ? mus[r_] : 0.0;
+                    const double g = im * c + lam_r;
+                    const double gj = (r.sign > 0) ? 1.0 : -1.0;
+                    if (ownx) { dxx = fma(gj * im, gj, dxx); ax = fma(gj, g, ax); }
+                    else { duu = fma(gj * im, gj, duu); au = fma(gj, g, au); }
+                }
+            } else {
+                const double gx = (j < n) ? row_jac_s(r, xs, j) : 0.0;
+                const double gu = (!term && j < m) ? row_jac_s(r, xs, n + j) : 0.0;
+                if (gx != 0.0 || gu != 0.0) {
+                    const double c = row_value_s(r, xs);
+                    const double lam_r = lams[r_];
+                    const bool act = r.eq ? true : ((c >= 0.0) || (lam_r > 0.0));
+                    const double im = act ? mus[r_] : 0.0;
+                    const double g = im * c + lam_r;
+                    if (gx != 0.0) {
+#pragma unroll
+                        for (int i = 0; i < n; i++) {
+                            const double gi = row_jac_s(r, xs, i);
+                            if (gi != 0.0) {
+                                if (i == j) dxx = fma(gi * im, gx, dxx);
+                                else Qxxc[i] = fma(gi * im, gx, Qxxc[i]);
+                            }
+                        }
+                        if (!term) {
+#pragma unroll
+                            for (int i = 0; i < m; i++) {
+                                const double gi = row_jac_s(r, xs, n + i);
+                                if (gi != 0.0) Quxc[i] = fma(gi * im, gx, Quxc[i]);
+                            }
+                        }
+                        ax = fma(gx, g, ax);
+                    }
+                    if (gu != 0.0) {
+#pragma unroll
+                        for (int i = 0; i < m; i++) {
+                            const double gi = row_jac_s(r, xs, n + i);
+                            if (gi != 0.0) {
+                                if (i == j) duu = fma(gi * im, gu, duu);
+                                else Quuc[i] = fma(gi * im, gu, Quuc[i]);
+                            }
+                        }
+                        au = fma(gu, g, au);
+                    }
+                }
+            }
+        }
+        // the wrapped quadratic cost: own entries of the unscaled gradients
         const double* Qm = term ? P.Qf : P.Q;
         const double* qv = term ? P.qf : P.q;
         const bool qd = term ? P.qf_diag : P.q_diag;
+        double vqx = 0.0, vqu = 0.0;
         if (j < nq) {
             double a = 0.0, bq = 0.0;
             if (qd) {
-#pragma unroll
-                for (int i = 0; i < nq; i++) if (i == j) a = fma(__ldg(&Qm[i * nq + i]), x[i], a);
+                a = fma(__ldg(&Qm[j * nq + j]), xs[j], a);
             } else {
 #pragma unroll
-                for (int i = 0; i < nq; i++) a = fma(__ldg(&Qm[i * nq + j]), x[i], a);
+                for (int i = 0; i < nq; i++) a = fma(__ldg(&Qm[i * nq + j]), xs[i], a);
             }
             if (!term && !P.h_zero) {
 #pragma unroll
-                for (int i = 0; i < mq; i++) bq = fma(__ldg(&P.H[j * mq + i]), u[i], bq);
+                for (int i = 0; i < mq; i++) bq = fma(__ldg(&P.H[j * mq + i]), xs[n + i], bq);
             }
-            sm.vQx[j] = term ? (a + __ldg(&qv[j])) : ((a + __ldg(&qv[j])) + bq);
+            vqx = term ? (a + __ldg(&qv[j])) : ((a + __ldg(&qv[j])) + bq);
         }
         if (!term && j < mq) {
             double a = 0.0, bq = 0.0;
             if (P.r_diag) {
-#pragma unroll
-                for (int i = 0; i < mq; i++) if (i == j) a = fma(__ldg(&P.R[i * mq + i]), u[i], a);
+                a = fma(__ldg(&P.R[j * mq + j]), xs[n + j], a);
             } else {
 #pragma unroll
-                for (int i = 0; i < mq; i++) a = fma(__ldg(&P.R[i * mq + j]), u[i], a);
+                for (int i = 0; i < mq; i++) a = fma(__ldg(&P.R[i * mq + j]), xs[n + i], a);
             }
             if (!P.h_zero) {
 #pragma unroll
-                for (int i = 0; i < nq; i++) bq = fma(__ldg(&P.H[i * mq + j]), x[i], bq);
+                for (int i = 0; i < nq; i++) bq = fma(__ldg(&P.H[i * mq + j]), xs[i], bq);
             }
-            sm.vQu[j] = (a + __ldg(&P.r[j])) + bq;
+            vqu = (a + __ldg(&P.r[j])) + bq;
         }
-        gsync();
         double dt = P.dt, tau = 0.0, l1 = 0.0;
-        if (C::MT && !term) {
-            tau = u[m - 1];
-            dt = tau * tau;
-            l1 = quad_stage<C>(P, x, u);
+        if constexpr (C::MT) {
+            if (!term) {
+                // the minimum-time blocks couple every lane's gradient entries: exchange them
+                if (j < nq) sm.vQx[j] = vqx;
+                if (j < mq) sm.vQu[j] = vqu;
+                gsync();
+                double x[n], u[m];
+#pragma unroll
+                for (int i = 0; i < n; i++) x[i] = xs[i];
+#pragma unroll
+                for (int i = 0; i < m; i++) u[i] = xs[n + i];
+                tau = u[m - 1];
+                dt = tau * tau;
+                l1 = quad_stage<C>(P, x, u);
+            }
         }
-        // base blocks, column j
+        // cost blocks, column j, added to the AL sums
         if (j < n) {
 #pragma unroll
             for (int i = 0; i < n; i++) {
                 double v = 0.0;
                 if (i < nq && j < nq) v = term ? __ldg(&Qm[j * nq + i]) : __ldg(&Qm[j * nq + i]) * dt;
                 if (C::MT && i == n - 1 && j == n - 1) v = P.R_mt;
-                Qxxc[i] = v;
+                const double acc = (i == j) ? dxx : Qxxc[i];
+                Qxxc[i] = has_al ? (v + acc) : v;
             }
             double v = 0.0;
-            if (j < nq) v = term ? sm.vQx[j] : sm.vQx[j] * dt;
-            if (C::MT && j == n - 1) v = P.R_mt * x[n - 1];
-            Qx_j = v;
+            if (j < nq) v = term ? vqx : vqx * dt;
+            if (C::MT && j == n - 1) v = P.R_mt * xs[n - 1];
+            Qx_j = has_al ? (v + ax) : v;
             if (!term) {
 #pragma unroll
                 for (int i = 0; i < m; i++) {  // ux is m×n, element (i,j)
                     double w = 0.0;
                     if (i < mq && j < nq) w = P.h_zero ? (0.0 * dt) : __ldg(&P.H[j * mq + i]) * dt;
-                    if (C::MT && i == m - 1 && j < nq) w = (2.0 * tau) * sm.vQx[j];
-                    Quxc[i] = w;
+                    if (C::MT && i == m - 1 && j < nq) w = (2.0 * tau) * vqx;
+                    Quxc[i] = has_al ? (w + Quxc[i]) : w;
                 }
             }
         }
@@ -475,76 +585,18 @@ struct BpGroup {
             for (int i = 0; i < m; i++) {
                 double v = 0.0;
                 if (i < mq && j < mq) v = __ldg(&P.R[j * mq + i]) * dt;
-                if (C::MT) {
+                if constexpr (C::MT) {
                     if (j == m - 1 && i < mq) v = (2.0 * tau) * sm.vQu[i];
-                    if (i == m - 1 && j < mq) v = (2.0 * tau) * sm.vQu[j];
+                    if (i == m - 1 && j < mq) v = (2.0 * tau) * vqu;
                     if (i == m - 1 && j == m - 1) v = 2.0 * l1 + P.R_mt;
                 }
-                Quuc[i] = v;
+                const double acc = (i == j) ? duu : Quuc[i];
+                Quuc[i] = has_al ? (v + acc) : v;
             }
             double v = 0.0;
-            if (j < mq) v = sm.vQu[j] * dt;
+            if (j < mq) v = vqu * dt;
             if (C::MT && j == m - 1) v = tau * (2.0 * l1 + P.R_mt);
-            Qu_j = v;
-        }
-        if (!al_on) return;
-        const int rb = P.knot_row_begin[k], rc = P.knot_row_count[k];
-        if (rc == 0) return;
-        const double* lamk = lams;
-        const double* muk = mus;
-        double axx[n], aux_[m], auu[m], ax = 0.0, au = 0.0;
-#pragma unroll
-        for (int i = 0; i < n; i++) axx[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < m; i++) { aux_[i] = 0.0; auu[i] = 0.0; }
-        for (int r_ = 0; r_ < rc; r_++) {
-            const DevRow r = P.rows[rb + r_];
-            const double gx = (j < n) ? row_jac<C>(r, x, j) : 0.0;
-            const double gu = (!term && j < m) ? row_jac<C>(r, x, n + j) : 0.0;
-            if (gx != 0.0 || gu != 0.0) {
-                const double c = row_value<C>(r, x, u);
-                const double lam_r = lamk[r_];
-                const bool act = r.eq ? true : ((c >= 0.0) || (lam_r > 0.0));
-                const double im = act ? muk[r_] : 0.0;
-                const double g = im * c + lam_r;
-                if (gx != 0.0) {
-#pragma unroll
-                    for (int i = 0; i < n; i++) {
-                        const double gi = row_jac<C>(r, x, i);
-                        if (gi != 0.0) axx[i] = fma(gi * im, gx, axx[i]);
-                    }
-                    if (!term) {
-#pragma unroll
-                        for (int i = 0; i < m; i++) {
-                            const double gi = row_jac<C>(r, x, n + i);
-                            if (gi != 0.0) aux_[i] = fma(gi * im, gx, aux_[i]);
-                        }
-                    }
-                    ax = fma(gx, g, ax);
-                }
-                if (gu != 0.0) {
-#pragma unroll
-                    for (int i = 0; i < m; i++) {
-                        const double gi = row_jac<C>(r, x, n + i);
-                        if (gi != 0.0) auu[i] = fma(gi * im, gu, auu[i]);
-                    }
-                    au = fma(gu, g, au);
-                }
-            }
-        }
-        if (j < n) {
-#pragma unroll
-            for (int i = 0; i < n; i++) Qxxc[i] += axx[i];
-            Qx_j += ax;
-            if (!term) {
-#pragma unroll
-                for (int i = 0; i < m; i++) Quxc[i] += aux_[i];
-            }
-        }
-        if (!term && j < m) {
-#pragma unroll
-            for (int i = 0; i < m; i++) Quuc[i] += auu[i];
-            Qu_j += au;
+            Qu_j = has_al ? (v + au) : v;
         }
     }
 
@@ -736,10 +788,6 @@ struct BpGroup {
                 gsync();  // knot k's inputs have landed; every lane is done with knot k+1
                 if (k > 0) prefetch(k - 1, buf ^ 1);
                 const double* AB = sm.AB[buf];
-                if (j < n) {
-#pragma unroll
-                    for (int l = 0; l < n; l++) Acol[l] = AB[l * LDZ + j];
-                }
                 if (store_mode && k >= stored_from) {
                     q_load(k);
                 } else {
@@ -751,7 +799,7 @@ struct BpGroup {
                 if (j < n) {
                     double acc = 0.0;
 #pragma unroll
-                    for (int l = 0; l < n; l++) acc = fma(Acol[l], sm.Sx[l], acc);
+                    for (int l = 0; l < n; l++) acc = fma(AB[l * LDZ + j], sm.Sx[l], acc);
                     Qx_j += acc;
                     double t[n], tu[m];
 #pragma unroll
@@ -787,7 +835,7 @@ struct BpGroup {
                     for (int i = 0; i < m; i++) a2[i] = 0.0;
 #pragma unroll
                     for (int l = 0; l < n; l++) {
-                        const double a_l = Acol[l];
+                        const double a_l = AB[l * LDZ + j];
 #pragma unroll
                         for (int i = 0; i < n; i++) a1[i] = fma(sm.T[l * LDn + i], a_l, a1[i]);
 #pragma unroll
@@ -953,7 +1001,7 @@ struct BpGroup {
 };
 
 template <class C, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS) ls_bp_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
+__global__ void __launch_bounds__(32 * WARPS, 3) ls_bp_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
     constexpr int GS = ls_group_size<C>();
     constexpr int GPB = (32 / GS) * WARPS;  // groups per block
     extern __shared__ __align__(16) unsigned char ls_smem_raw[];
@@ -1305,12 +1353,22 @@ template <class C> int ls_setup_fn(int sm_count, LsGrids* g) {
     g->bp_groups_per_block = GPB;
     g->trial_group = LS_TRIAL_G;
     if (cudaFuncSetAttribute(ls_bp_kernel<C, LS_BP_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->bp_smem) != cudaSuccess) return -1;
+    cudaFuncSetAttribute(ls_bp_kernel<C, LS_BP_WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_init_kernel<C>, 32, 0);
     g->init = sm_count * (nb > 0 ? nb : 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_outer_kernel<C>, 32, 0);
     g->outer = sm_count * (nb > 0 ? nb : 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_jac_kernel<C>, 128, 0);
+    g->jac_pc = C::PC;
+    if constexpr (C::MODEL == 4) {  // quadrotor: partial directions per thread tunable at run time (1, 2 or 3)
+        if (const char* env = getenv("TRAJOPT_B200_JAC_PC")) {
+            const int v = atoi(env);
+            if (v == 1 || v == 3) g->jac_pc = v;
+        }
+    }
+    if (C::MODEL == 4 && g->jac_pc == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_jac_kernel<C, (C::MODEL == 4) ? 1 : C::PC>, 128, 0);
+    else if (C::MODEL == 4 && g->jac_pc == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_jac_kernel<C, (C::MODEL == 4) ? 3 : C::PC>, 128, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_jac_kernel<C, C::PC>, 128, 0);
     g->jac = sm_count * (nb > 0 ? nb : 1);
     g->occ_jac = nb;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_bp_kernel<C, LS_BP_WARPS>, 32 * LS_BP_WARPS, g->bp_smem);
@@ -1329,9 +1387,14 @@ template <class C> void ls_launch_fn(int phase, const LsGrids& g, cudaStream_t s
                                      const LsCtl& lc, int cur, int grp) {
     switch (phase) {
         case LS_PHASE_INIT: ls_init_kernel<C><<<g.init, 32, 0, st>>>(P, B, c, lc); break;
-        case LS_PHASE_JAC: ls_jac_kernel<C><<<g.jac, 128, 0, st>>>(P, lc, cur); break;
+        case LS_PHASE_JAC:
+            if (C::MODEL == 4 && g.jac_pc == 1) ls_jac_kernel<C, (C::MODEL == 4) ? 1 : C::PC><<<g.jac, 128, 0, st>>>(P, lc, cur);
+            else if (C::MODEL == 4 && g.jac_pc == 3) ls_jac_kernel<C, (C::MODEL == 4) ? 3 : C::PC><<<g.jac, 128, 0, st>>>(P, lc, cur);
+            else ls_jac_kernel<C, C::PC><<<g.jac, 128, 0, st>>>(P, lc, cur);
+            break;
         case LS_PHASE_BP: ls_bp_kernel<C, LS_BP_WARPS><<<g.bp, 32 * LS_BP_WARPS, g.bp_smem, st>>>(P, c, lc, cur); break;
         case LS_PHASE_TRIAL: ls_trial_kernel<C, LS_TRIAL_G><<<g.trial, 128, 0, st>>>(P, B, c, lc, cur, grp); break;
+        case LS_PHASE_TRIAL_ALL: ls_trial_kernel<C, 32><<<g.trial, 128, 0, st>>>(P, B, c, lc, cur, 0); break;
         case LS_PHASE_ACCEPT: ls_accept_kernel<C><<<g.accept, 64, 0, st>>>(P, B, c, lc, cur); break;
         case LS_PHASE_OUTER: ls_outer_kernel<C><<<g.outer, 32, 0, st>>>(P, B, c, lc, cur); break;
     }
