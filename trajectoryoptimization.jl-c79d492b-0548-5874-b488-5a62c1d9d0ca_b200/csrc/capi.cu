@@ -328,6 +328,7 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
     unsigned int known_active = (unsigned int)s->B;  // upper bound (the list only shrinks), refreshed LAG ticks late
     // diagnostics: TRAJOPT_B200_TICK_LOG=<file> records one event per tick and writes "tick ms active" lines
     const char* tick_log = getenv("TRAJOPT_B200_TICK_LOG");
+    const bool phase_log = tick_log && getenv("TRAJOPT_B200_TICK_DETAIL");
     std::vector<cudaEvent_t> tick_ev;
     std::vector<unsigned int> tick_active;
     auto dump_ticks = [&]() {
@@ -335,11 +336,17 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
         cudaStreamSynchronize(st);
         FILE* f = fopen(tick_log, "a");
         if (f) {
-            fprintf(f, "# solve B=%d ticks=%zu\n", s->B, tick_ev.size() - 1);
-            for (size_t i = 1; i < tick_ev.size(); i++) {
-                float ms = 0.f;
-                cudaEventElapsedTime(&ms, tick_ev[i - 1], tick_ev[i]);
-                fprintf(f, "%zu %.4f %u\n", i - 1, ms, i - 1 < tick_active.size() ? tick_active[i - 1] : 0u);
+            const size_t per = phase_log ? 5 : 1;  // events per tick: [jac, bp, trials, accept,] outer
+            fprintf(f, "# solve B=%d ticks=%zu%s\n", s->B, (tick_ev.size() - 1) / per, phase_log ? " columns: tick jac bp trial accept outer active" : "");
+            for (size_t i = 1; i + per - 1 < tick_ev.size(); i += per) {
+                const size_t tk = (i - 1) / per;
+                fprintf(f, "%zu", tk);
+                for (size_t q = 0; q < per; q++) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, tick_ev[i + q - 1], tick_ev[i + q]);
+                    fprintf(f, " %.4f", ms);
+                }
+                fprintf(f, " %u\n", tk < tick_active.size() ? tick_active[tk] : 0u);
             }
             fclose(f);
         }
@@ -351,10 +358,19 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
         cudaEventRecord(e, st);
         tick_ev.push_back(e);
     }
+    auto mark = [&]() {
+        if (!phase_log) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tick_ev.push_back(e);
+    };
     for (long long t = 0; t < max_ticks; t++) {
         const int cur = (int)(t & 1);
         v.ki->ls_launch(LS_PHASE_JAC, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+        mark();
         v.ki->ls_launch(LS_PHASE_BP, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+        mark();
         if (known_active <= tail_threshold && ntrial <= 32) {
             v.ki->ls_launch(LS_PHASE_TRIAL_ALL, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
             s->launches -= ngroups - 1;
@@ -364,7 +380,9 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
                 v.ki->ls_launch(LS_PHASE_TRIAL, v.grids, st, v.P, Bt, c, v.lc, cur, g);
             }
         }
+        mark();
         v.ki->ls_launch(LS_PHASE_ACCEPT, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+        mark();
         v.ki->ls_launch(LS_PHASE_OUTER, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
         CK_RET(s, cudaGetLastError());
         s->launches += 4 + ngroups;

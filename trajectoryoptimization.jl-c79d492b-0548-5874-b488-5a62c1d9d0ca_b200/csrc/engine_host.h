@@ -97,6 +97,7 @@ struct LsGrids {
     int bp_smem, bp_groups_per_block, trial_group;
     int occ_jac, occ_bp, occ_trial;
     int jac_pc;  // partial directions per thread in the Jacobian kernel
+    int jac_minb, trial_minb;  // __launch_bounds__ min-blocks variants (register caps)
 };
 
 // host-visible launcher table entry

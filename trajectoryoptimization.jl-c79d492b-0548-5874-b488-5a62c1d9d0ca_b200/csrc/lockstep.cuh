@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(32) ls_outer_kernel(const DevProblem P, const 
 }
 
 // ---- Jacobians: thread per (problem, knot, chunk of partial directions) -----------------------
-template <class C, int PC>
-__global__ void __launch_bounds__(128) ls_jac_kernel(const DevProblem P, const LsCtl lc, const int cur) {
+template <class C, int PC, int MINB>
+__global__ void __launch_bounds__(128, MINB) ls_jac_kernel(const DevProblem P, const LsCtl lc, const int cur) {
     constexpr int NCH = (C::PT + PC - 1) / PC;
     typedef Dual<PC> D;
     const unsigned int na = lc.counts[cur];
@@ -1129,8 +1129,8 @@ struct Rollout {
 };
 
 // group `grp` of G step sizes: trials grp*G .. grp*G+G-1 (alpha = 2^-trial)
-template <class C, int G>
-__global__ void __launch_bounds__(128) ls_trial_kernel(const DevProblem P, const DevBatch Bt, const DevCtl ctl, const LsCtl lc,
+template <class C, int G, int MINB>
+__global__ void __launch_bounds__(128, MINB) ls_trial_kernel(const DevProblem P, const DevBatch Bt, const DevCtl ctl, const LsCtl lc,
                                                        const int cur, const int grp) {
     const int* list = (grp == 0) ? lc.list[cur] : lc.retry[(grp - 1) & 1];
     const unsigned int na = (grp == 0) ? lc.counts[cur] : lc.counts[2 + ((grp - 1) & 1)];
@@ -1345,6 +1345,22 @@ __global__ void __launch_bounds__(64) ls_accept_kernel(const DevProblem P, const
 constexpr int LS_BP_WARPS = 4;
 constexpr int LS_TRIAL_G = 8;
 
+typedef void (*LsJacFn)(const DevProblem, const LsCtl, const int);
+typedef void (*LsTrialFn)(const DevProblem, const DevBatch, const DevCtl, const LsCtl, const int, const int);
+template <class C> LsJacFn ls_jac_variant(int pc, int minb) {
+    if constexpr (C::MODEL == 4) {
+        if (pc == 1) return minb == 4 ? ls_jac_kernel<C, 1, 4> : (minb == 3 ? ls_jac_kernel<C, 1, 3> : ls_jac_kernel<C, 1, 2>);
+        if (pc == 2) return minb == 4 ? ls_jac_kernel<C, 2, 4> : (minb == 3 ? ls_jac_kernel<C, 2, 3> : ls_jac_kernel<C, 2, 2>);
+    }
+    return ls_jac_kernel<C, C::PC, 2>;
+}
+template <class C> LsTrialFn ls_trial_variant(int minb, bool all) {
+    if constexpr (C::MODEL == 4) {
+        if (minb == 4) return all ? ls_trial_kernel<C, 32, 4> : ls_trial_kernel<C, LS_TRIAL_G, 4>;
+    }
+    return all ? ls_trial_kernel<C, 32, 3> : ls_trial_kernel<C, LS_TRIAL_G, 3>;
+}
+
 template <class C> unsigned long long ls_ws_doubles_fn(int N, int Ptot) { return ws_layout<C>(N, Ptot, false).total; }
 
 template <class C> int ls_setup_fn(int sm_count, LsGrids* g) {
@@ -1360,22 +1376,21 @@ template <class C> int ls_setup_fn(int sm_count, LsGrids* g) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_outer_kernel<C>, 32, 0);
     g->outer = sm_count * (nb > 0 ? nb : 1);
     g->jac_pc = C::PC;
-    if constexpr (C::MODEL == 4) {  // quadrotor: partial directions per thread tunable at run time (1, 2 or 3)
-        if (const char* env = getenv("TRAJOPT_B200_JAC_PC")) {
-            const int v = atoi(env);
-            if (v == 1 || v == 3) g->jac_pc = v;
-        }
+    g->jac_minb = 2;
+    g->trial_minb = 3;
+    if constexpr (C::MODEL == 4) {  // quadrotor: kernel variants selectable at run time (tuning)
+        if (const char* env = getenv("TRAJOPT_B200_JAC_PC")) { const int v = atoi(env); if (v == 1 || v == 2) g->jac_pc = v; }
+        if (const char* env = getenv("TRAJOPT_B200_JAC_MINB")) { const int v = atoi(env); if (v >= 2 && v <= 4) g->jac_minb = v; }
+        if (const char* env = getenv("TRAJOPT_B200_TRIAL_MINB")) { const int v = atoi(env); if (v == 3 || v == 4) g->trial_minb = v; }
     }
-    if (C::MODEL == 4 && g->jac_pc == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_jac_kernel<C, (C::MODEL == 4) ? 1 : C::PC>, 128, 0);
-    else if (C::MODEL == 4 && g->jac_pc == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_jac_kernel<C, (C::MODEL == 4) ? 3 : C::PC>, 128, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_jac_kernel<C, C::PC>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_jac_variant<C>(g->jac_pc, g->jac_minb), 128, 0);
     g->jac = sm_count * (nb > 0 ? nb : 1);
     g->occ_jac = nb;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_bp_kernel<C, LS_BP_WARPS>, 32 * LS_BP_WARPS, g->bp_smem);
     if (nb < 1) return -2;
     g->bp = sm_count * nb;
     g->occ_bp = nb;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_trial_kernel<C, LS_TRIAL_G>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_trial_variant<C>(g->trial_minb, false), 128, 0);
     g->trial = sm_count * (nb > 0 ? nb : 1);
     g->occ_trial = nb;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_accept_kernel<C>, 64, 0);
@@ -1387,14 +1402,10 @@ template <class C> void ls_launch_fn(int phase, const LsGrids& g, cudaStream_t s
                                      const LsCtl& lc, int cur, int grp) {
     switch (phase) {
         case LS_PHASE_INIT: ls_init_kernel<C><<<g.init, 32, 0, st>>>(P, B, c, lc); break;
-        case LS_PHASE_JAC:
-            if (C::MODEL == 4 && g.jac_pc == 1) ls_jac_kernel<C, (C::MODEL == 4) ? 1 : C::PC><<<g.jac, 128, 0, st>>>(P, lc, cur);
-            else if (C::MODEL == 4 && g.jac_pc == 3) ls_jac_kernel<C, (C::MODEL == 4) ? 3 : C::PC><<<g.jac, 128, 0, st>>>(P, lc, cur);
-            else ls_jac_kernel<C, C::PC><<<g.jac, 128, 0, st>>>(P, lc, cur);
-            break;
+        case LS_PHASE_JAC: ls_jac_variant<C>(g.jac_pc, g.jac_minb)<<<g.jac, 128, 0, st>>>(P, lc, cur); break;
         case LS_PHASE_BP: ls_bp_kernel<C, LS_BP_WARPS><<<g.bp, 32 * LS_BP_WARPS, g.bp_smem, st>>>(P, c, lc, cur); break;
-        case LS_PHASE_TRIAL: ls_trial_kernel<C, LS_TRIAL_G><<<g.trial, 128, 0, st>>>(P, B, c, lc, cur, grp); break;
-        case LS_PHASE_TRIAL_ALL: ls_trial_kernel<C, 32><<<g.trial, 128, 0, st>>>(P, B, c, lc, cur, 0); break;
+        case LS_PHASE_TRIAL: ls_trial_variant<C>(g.trial_minb, false)<<<g.trial, 128, 0, st>>>(P, B, c, lc, cur, grp); break;
+        case LS_PHASE_TRIAL_ALL: ls_trial_variant<C>(g.trial_minb, true)<<<g.trial, 128, 0, st>>>(P, B, c, lc, cur, 0); break;
         case LS_PHASE_ACCEPT: ls_accept_kernel<C><<<g.accept, 64, 0, st>>>(P, B, c, lc, cur); break;
         case LS_PHASE_OUTER: ls_outer_kernel<C><<<g.outer, 32, 0, st>>>(P, B, c, lc, cur); break;
     }
