@@ -113,6 +113,46 @@ def _pend_mintime(B):
     return p, o, np.broadcast_to(p.x0, (B, 2)).copy() + 0.05 * problems.batch_x0("pendulum", B), None
 
 
+def _sqrt_opts(**al_kw):
+    il = api.iLQRSolverOptions(square_root=True)
+    return api.AugmentedLagrangianSolverOptions(opts_uncon=il, **al_kw)
+
+
+def _pend_sqrt_altro(B):
+    """square-root backward pass (backward_pass.jl:87-169) in a full ALTRO solve: pendulum with bounds + goal"""
+    p = problems.pendulum()
+    return p, api.ALTROSolverOptions(opts_al=_sqrt_opts()), problems.batch_x0("pendulum", B) * 0.2, None
+
+
+def _dp_sqrt_ilqr(B):
+    p = problems.doublependulum()
+    return p, api.iLQRSolverOptions(square_root=True), problems.batch_x0("doublependulum", B), None
+
+
+def _acrobot_sqrt_al(B):
+    p = problems.acrobot()
+    x0 = problems.batch_x0("acrobot", B)
+    x0[0] = 0.0
+    return p, _sqrt_opts(iterations=30, penalty_scaling=10.0), x0, None
+
+
+def _sqrt_mintime(which):
+    """BASELINE config 5: square-root backward pass + minimum time: +-20 torque bounds (needed by
+    minimum_time.jl:6), tf = 0, R_minimum_time = 15, dt_max = 0.02, dt_min = 1e-3.  Per-problem NOT_PD statuses are
+    expected; parity = same status."""
+    def make(B):
+        p = problems.acrobot() if which == "acrobot" else problems.doublependulum()
+        n, m = p.model.n, p.model.m
+        bnd = api.BoundConstraint(n, m, u_min=-20.0, u_max=20.0)
+        for k in range(p.N - 1):
+            p.constraints.add(k, bnd)
+        p.tf = 0.0
+        o = api.ALTROSolverOptions(opts_al=_sqrt_opts(), R_minimum_time=15.0, dt_max=0.02, dt_min=1e-3)
+        x0 = problems.batch_x0(which if which == "acrobot" else "doublependulum", B)
+        return p, o, x0, None
+    return make
+
+
 CASES = {
     "di_altro": _di,
     "pend_ilqr": _pend_ilqr,
@@ -129,4 +169,9 @@ CASES = {
     "park_altro": _park,
     "park_inf_altro": _park_inf,
     "pend_mintime": _pend_mintime,
+    "pend_sqrt_altro": _pend_sqrt_altro,
+    "dp_sqrt_ilqr": _dp_sqrt_ilqr,
+    "acrobot_sqrt_al": _acrobot_sqrt_al,
+    "acrobot_sqrt_mintime": _sqrt_mintime("acrobot"),
+    "dp_sqrt_mintime": _sqrt_mintime("doublependulum"),
 }

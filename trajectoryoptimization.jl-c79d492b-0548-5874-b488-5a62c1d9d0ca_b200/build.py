@@ -65,7 +65,7 @@ def generate():
 
 def _deps_hash():
     h = hashlib.sha1()
-    for f in ("engine.cuh", "lockstep.cuh", "engine_host.h", "models.cuh", "capi.cu", "peak.cu", "../build.py", "../../include/trajopt_b200.h"):
+    for f in ("engine.cuh", "lockstep.cuh", "sqrt_bp.cuh", "engine_host.h", "models.cuh", "capi.cu", "peak.cu", "../build.py", "../../include/trajopt_b200.h"):
         h.update(open(os.path.join(CSRC, f), "rb").read())
     return h.hexdigest()
 

@@ -369,7 +369,7 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
         const int cur = (int)(t & 1);
         v.ki->ls_launch(LS_PHASE_JAC, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
         mark();
-        v.ki->ls_launch(LS_PHASE_BP, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+        v.ki->ls_launch(c.o.opts_uncon.square_root ? LS_PHASE_BP_SQRT : LS_PHASE_BP, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
         mark();
         if (known_active <= tail_threshold && ntrial <= 32) {
             v.ki->ls_launch(LS_PHASE_TRIAL_ALL, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
@@ -463,7 +463,10 @@ int launch(TOSolver* s, int which, int mode, const TOALOptions& alo, bool altro_
     rc = ensure_engine_buffers(s, v);
     if (rc) return rc;
     c.ws = v.ws; c.ws_stride = v.ws_stride;
-    if (s->engine == 1) return run_lockstep(s, v, Bt, c);
+    if (s->engine == 1) {
+        c.debug = (s->debug_doubles >= 16) ? s->debug : nullptr;  // lockstep: cycle profile of one backward-pass group
+        return run_lockstep(s, v, Bt, c);
+    }
     CK_RET(s, cudaMemsetAsync(s->queue, 0, sizeof(unsigned int), s->stream));
     v.ki->launch(v.grid, s->stream, v.P, Bt, c);
     CK_RET(s, cudaGetLastError());
@@ -475,7 +478,8 @@ int check_opts(TOSolver* s, const TOALOptions& o) {
     const TOiLQROptions& io = o.opts_uncon;
     if (io.iterations_linesearch < 0 || io.iterations_linesearch > 31)
         return s->fail(TO_ERR_UNSUPPORTED, "iterations_linesearch must be in [0,31] (one warp lane per step size)");
-    if (io.square_root) return s->fail(TO_ERR_UNSUPPORTED, "square_root backward pass is not built into this library yet");
+    if (io.square_root && s->engine != 1)
+        return s->fail(TO_ERR_UNSUPPORTED, "the square-root backward pass runs on the lockstep engine only (unset TRAJOPT_B200_ENGINE)");
     if (!s->batch_set) return s->fail(TO_ERR_INVALID, "to_set_batch has not been called");
     return 0;
 }

@@ -91,13 +91,13 @@ struct LsCtl {
     unsigned long long ws_stride;  // doubles per problem
 };
 
-enum { LS_PHASE_INIT = 0, LS_PHASE_JAC, LS_PHASE_BP, LS_PHASE_TRIAL, LS_PHASE_ACCEPT, LS_PHASE_OUTER, LS_PHASE_TRIAL_ALL };
+enum { LS_PHASE_INIT = 0, LS_PHASE_JAC, LS_PHASE_BP, LS_PHASE_TRIAL, LS_PHASE_ACCEPT, LS_PHASE_OUTER, LS_PHASE_TRIAL_ALL, LS_PHASE_BP_SQRT };
 struct LsGrids {
     int init, jac, bp, trial, accept, outer;  // grid sizes (persistent, grid-stride)
     int bp_smem, bp_groups_per_block, trial_group;
     int occ_jac, occ_bp, occ_trial;
     int jac_pc;  // partial directions per thread in the Jacobian kernel
-    int jac_minb, trial_minb;  // __launch_bounds__ min-blocks variants (register caps)
+    int jac_minb, trial_minb, bp_minb;  // __launch_bounds__ min-blocks variants (register caps)
 };
 
 // host-visible launcher table entry

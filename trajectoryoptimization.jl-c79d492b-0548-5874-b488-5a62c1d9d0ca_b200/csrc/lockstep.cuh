@@ -20,6 +20,7 @@
 // assignment of work to lanes differs, the expression trees do not.
 #pragma once
 #include "engine.cuh"
+#include "sqrt_bp.cuh"
 
 namespace tob {
 
@@ -320,10 +321,10 @@ struct alignas(16) BpSmem {
     static constexpr int LDZ = C::LDZ;
     static constexpr int XU = (n + m + 1) & ~1;
     static constexpr int LAMCAP = 16;          // multipliers / penalties of one knot staged by the prefetch (larger sets read global)
-    // double-buffered per-knot inputs, filled by cp.async one knot ahead
-    double AB[2][n * LDZ];   // row l = [A(l,0..n-1) B(l,0..m-1)]
-    double xu[2][XU];        // [x_k ; u_k]
-    double lam[2][LAMCAP], mu[2][LAMCAP];
+    // per-knot inputs, filled by cp.async while the previous knot's factorisation / cost-to-go update runs
+    double AB[n * LDZ];      // row l = [A(l,0..n-1) B(l,0..m-1)]
+    double xu[XU];           // [x_k ; u_k]
+    double lam[LAMCAP], mu[LAMCAP];
     // products streamed by the other lanes of the group (all "left operand, contiguous in the output row index")
     double T[n * LDn];       // T(i,l) at [l*LDn+i]; later the unsymmetrised S.xx
     double Tu[n * LDm];      // Tu(i,l) at [l*LDm+i]
@@ -332,6 +333,11 @@ struct alignas(16) BpSmem {
     double KQ[m * LDn];      // KQ(i,l)  at [l*LDn+i]
     double Quu[m * m], Sx[n], Qu[m], d[m], vQx[C::nq], vQu[C::mq], xN[n];
 };
+// byte stride between the shared-memory blocks of consecutive lane groups: ≡ 64 (mod 128), so the two groups of a
+// warp never read different addresses that fall into the same banks
+template <class C> __host__ __device__ constexpr int ls_bp_stride() {
+    return (int)(((sizeof(BpSmem<C>) + 63) / 128) * 128 + 64);
+}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -361,6 +367,16 @@ struct BpGroup {
     // register-resident columns
     double Scol[n], Qxxc[n], Quxc[m], Quuc[m], Kcol[m];
     double Qx_j, Qu_j, Sx_j;
+    // optional cycle profile of one group (diagnostics: to_debug_enable): cycles per section of the knot loop
+    long long* prof = nullptr;
+    long long pt0 = 0;
+    __device__ void tick(int section) {
+        if (prof) {
+            const long long t = clock64();
+            if (j == 0) prof[section] += t - pt0;
+            pt0 = clock64();
+        }
+    }
 
     __device__ BpGroup(const DevProblem& P_, BpSmem<C>& s_, double* ws_, int j_, unsigned gmask_, bool al_on_, const TOiLQROptions& io_)
         : P(P_), sm(s_), ws(ws_), L(ws_layout<C>(P_.N, P_.Ptot, false)), j(j_), gmask(gmask_), al_on(al_on_), io(io_) {}
@@ -378,19 +394,19 @@ struct BpGroup {
         }
     }
 
-    // asynchronous copy of knot k's inputs ([A B], x, u, lambda, mu) into buffer `buf`
-    __device__ void prefetch(int k, int buf) {
+    // asynchronous copy of knot k's inputs ([A B], x, u, lambda, mu) into shared memory
+    __device__ void prefetch(int k) {
         const double* ab = ws + L.Z + (size_t)k * C::ZA;  // 16-byte aligned, C::ZA even
-        for (int e = 2 * j; e < C::ZA; e += 2 * GS) cp_async16(&sm.AB[buf][e], ab + e);
+        for (int e = 2 * j; e < C::ZA; e += 2 * GS) cp_async16(&sm.AB[e], ab + e);
         const double* xk = ws + L.X + (size_t)k * n;
         const double* uk = ws + L.U + (size_t)k * m;
-        for (int e = j; e < n + m; e += GS) cp_async8(&sm.xu[buf][e], (e < n) ? (xk + e) : (uk + (e - n)));
+        for (int e = j; e < n + m; e += GS) cp_async8(&sm.xu[e], (e < n) ? (xk + e) : (uk + (e - n)));
         if (al_on) {
             const int rc = P.knot_row_count[k], lo = P.knot_lam_off[k];
             if (rc <= LAMCAP) {
                 for (int e = j; e < rc; e += GS) {
-                    cp_async8(&sm.lam[buf][e], ws + L.LAM + lo + e);
-                    cp_async8(&sm.mu[buf][e], ws + L.MU + lo + e);
+                    cp_async8(&sm.lam[e], ws + L.LAM + lo + e);
+                    cp_async8(&sm.mu[e], ws + L.MU + lo + e);
                 }
             }
         }
@@ -632,9 +648,11 @@ struct BpGroup {
         }
     }
 
-    // isposdef(Hermitian(A)) — same code as Solver::chol_pd
+    // isposdef(Hermitian(A)): the arithmetic of Solver::chol_pd without its early exit (a failed pivot makes the
+    // later entries NaN, which nobody reads; only the verdict is used)
     __device__ bool chol_pd(const double* Areg) {
         double Uc[m * m];
+        bool pd = true;
 #pragma unroll
         for (int c = 0; c < m; c++) {
 #pragma unroll
@@ -648,10 +666,10 @@ struct BpGroup {
 #pragma unroll
             for (int l = 0; l < c; l++) acc = fma(Uc[c * m + l], Uc[c * m + l], acc);
             const double dd = Areg[c * m + c] - acc;
-            if (!(dd > 0.0)) return false;
+            pd = pd && (dd > 0.0);
             Uc[c * m + c] = sqrt(dd);
         }
-        return true;
+        return pd;
     }
     struct LU {
         double a[m * m];
@@ -766,7 +784,7 @@ struct BpGroup {
         for (;;) {
             cp_async_wait_all();
             gsync();
-            prefetch(N - 2, (N - 2) & 1);
+            prefetch(N - 2);
             // terminal cost-to-go: S = Qxx_N, Sx = Qx_N
             if (j < n) sm.xN[j] = ws[L.X + (size_t)(N - 1) * n + j];
             gsync();
@@ -783,18 +801,19 @@ struct BpGroup {
             dV1 = 0.0;
             bool failed = false;
             for (int k = N - 2; k >= 0; k--) {
-                const int buf = k & 1;
+                if (prof) pt0 = clock64();
                 cp_async_wait_all();
                 gsync();  // knot k's inputs have landed; every lane is done with knot k+1
-                if (k > 0) prefetch(k - 1, buf ^ 1);
-                const double* AB = sm.AB[buf];
+                const double* AB = sm.AB;
+                tick(0);
                 if (store_mode && k >= stored_from) {
                     q_load(k);
                 } else {
                     const int rc = P.knot_row_count[k], lo = P.knot_lam_off[k];
                     const bool staged = (rc <= LAMCAP);
-                    expansion(k, sm.xu[buf], staged ? sm.lam[buf] : ws + L.LAM + lo, staged ? sm.mu[buf] : ws + L.MU + lo);
+                    expansion(k, sm.xu, staged ? sm.lam : ws + L.LAM + lo, staged ? sm.mu : ws + L.MU + lo);
                 }
+                tick(1);
                 // Qx += A'Sx ; Qu += B'Sx ; T = A'S (column j) ; Tu = B'S (column j)
                 if (j < n) {
                     double acc = 0.0;
@@ -826,6 +845,7 @@ struct BpGroup {
                     Qu_j += acc;
                 }
                 gsync();
+                tick(2);
                 // Qxx += T*A ; Qux += Tu*A ; Quu += Tu*B
                 if (j < n) {
                     double a1[n], a2[m];
@@ -859,6 +879,7 @@ struct BpGroup {
 #pragma unroll
                     for (int i = 0; i < m; i++) Quuc[i] += a3[i];
                 }
+                tick(3);
                 if (store_mode) {
                     q_store(k);
                     if (k < stored_from) stored_from = k;
@@ -874,6 +895,10 @@ struct BpGroup {
                     for (int l = 0; l < m; l++) sm.QuxT[l * LDn + j] = Quxc[l];
                 }
                 gsync();
+                // every lane is done with this knot's [A B], x, u, multipliers: fetch the next knot's while the
+                // factorisation and the cost-to-go update run
+                if (k > 0) prefetch(k - 1);
+                tick(4);
                 // Quu_reg = Quu + rho*I, replicated per lane
                 double Quu[m * m];
                 LU f;
@@ -881,8 +906,12 @@ struct BpGroup {
                 for (int e = 0; e < m * m; e++) { Quu[e] = sm.Quu[e]; f.a[e] = Quu[e]; }
 #pragma unroll
                 for (int i = 0; i < m; i++) f.a[i * m + i] = Quu[i * m + i] + rho * 1.0;
-                if (!chol_pd(f.a)) { failed = true; break; }
+                // the positive-definiteness test and the LU factorisation are independent: no branch between them,
+                // so their dependent chains (sqrt / divide latencies) overlap
+                const bool pd = chol_pd(f.a);
                 lu_factor(f);
+                if (!pd) { failed = true; break; }
+                tick(5);
                 if (j < n) {
                     double rhs[m];
 #pragma unroll
@@ -915,6 +944,7 @@ struct BpGroup {
                     }
                 }
                 gsync();
+                tick(6);
                 double dk[m], Quv[m];
 #pragma unroll
                 for (int i = 0; i < m; i++) { dk[i] = sm.d[i]; Quv[i] = sm.Qu[i]; }
@@ -961,6 +991,7 @@ struct BpGroup {
                     sm.Sx[j] = Sx_j;
                 }
                 gsync();
+                tick(7);
                 if (j < n) {
 #pragma unroll
                     for (int i = 0; i < n; i++) Scol[i] = 0.5 * (Scol[i] + sm.T[i * LDn + j]);
@@ -981,6 +1012,7 @@ struct BpGroup {
                     }
                     dV1 += acc;
                 }
+                tick(8);
             }
             if (!failed) break;
             if (!store_mode) {
@@ -1000,12 +1032,12 @@ struct BpGroup {
     }
 };
 
-template <class C, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, 3) ls_bp_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
+template <class C, int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB) ls_bp_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
     constexpr int GS = ls_group_size<C>();
     constexpr int GPB = (32 / GS) * WARPS;  // groups per block
     extern __shared__ __align__(16) unsigned char ls_smem_raw[];
-    BpSmem<C>* smem = reinterpret_cast<BpSmem<C>*>(ls_smem_raw);
+    BpSmem<C>& smem_g = *reinterpret_cast<BpSmem<C>*>(ls_smem_raw + (size_t)(threadIdx.x / GS) * ls_bp_stride<C>());
     const unsigned int na = lc.counts[cur];
     const int g = threadIdx.x / GS, j = threadIdx.x % GS;
     const int lane = threadIdx.x & 31;
@@ -1017,9 +1049,10 @@ __global__ void __launch_bounds__(32 * WARPS, 3) ls_bp_kernel(const DevProblem P
             const int b = lc.list[cur][a];
             LsState* st = &lc.st[b];
             TOiLQROptions io = ctl.o.opts_uncon;
-            BpGroup<C> G(P, smem[g], lc.ws + (size_t)b * lc.ws_stride, j, gmask, al_on, io);
+            BpGroup<C> G(P, smem_g, lc.ws + (size_t)b * lc.ws_stride, j, gmask, al_on, io);
             G.rho = st->rho;
             G.drho = st->drho;
+            if (ctl.debug && a == 0) G.prof = reinterpret_cast<long long*>(ctl.debug);
             double dV0, dV1;
             const bool ok = G.run(dV0, dV1);
             if (j == 0) {
@@ -1208,9 +1241,10 @@ __global__ void __launch_bounds__(64) ls_accept_kernel(const DevProblem P, const
         bool copied = false;
         double rho = st->rho, drho = st->drho;
         if (st->bp_fail) {
-            // the reference would restart its backward pass forever (TO_STATUS_REG_DIVERGED): abort this solve
+            // 1: the reference would restart its backward pass forever (TO_STATUS_REG_DIVERGED); 2: PosDefException in the
+            // square-root pass (TO_STATUS_NOT_PD_SQRT).  Either way the reference aborts the solve here.
+            st->status |= (st->bp_fail == 2) ? TO_STATUS_NOT_PD_SQRT : TO_STATUS_REG_DIVERGED;
             st->bp_fail = 0;
-            st->status |= TO_STATUS_REG_DIVERGED;
             st->winner = -1;
             st->inner_ok = 0;
             ls_append(lc.outer_list, &lc.counts[4], b);
@@ -1347,6 +1381,13 @@ constexpr int LS_TRIAL_G = 8;
 
 typedef void (*LsJacFn)(const DevProblem, const LsCtl, const int);
 typedef void (*LsTrialFn)(const DevProblem, const DevBatch, const DevCtl, const LsCtl, const int, const int);
+typedef void (*LsBpFn)(const DevProblem, const DevCtl, const LsCtl, const int);
+template <class C> LsBpFn ls_bp_variant(int minb) {
+    if constexpr (C::MODEL == 4) {
+        if (minb == 4) return ls_bp_kernel<C, LS_BP_WARPS, 4>;
+    }
+    return ls_bp_kernel<C, LS_BP_WARPS, 3>;
+}
 template <class C> LsJacFn ls_jac_variant(int pc, int minb) {
     if constexpr (C::MODEL == 4) {
         if (pc == 1) return minb == 4 ? ls_jac_kernel<C, 1, 4> : (minb == 3 ? ls_jac_kernel<C, 1, 3> : ls_jac_kernel<C, 1, 2>);
@@ -1365,11 +1406,15 @@ template <class C> unsigned long long ls_ws_doubles_fn(int N, int Ptot) { return
 
 template <class C> int ls_setup_fn(int sm_count, LsGrids* g) {
     constexpr int GPB = (32 / ls_group_size<C>()) * LS_BP_WARPS;
-    g->bp_smem = (int)(sizeof(BpSmem<C>) * GPB);
+    g->bp_smem = ls_bp_stride<C>() * GPB;
     g->bp_groups_per_block = GPB;
     g->trial_group = LS_TRIAL_G;
-    if (cudaFuncSetAttribute(ls_bp_kernel<C, LS_BP_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->bp_smem) != cudaSuccess) return -1;
-    cudaFuncSetAttribute(ls_bp_kernel<C, LS_BP_WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    g->bp_minb = 3;
+    if constexpr (C::MODEL == 4) {
+        if (const char* env = getenv("TRAJOPT_B200_BP_MINB")) { const int v = atoi(env); if (v == 3 || v == 4) g->bp_minb = v; }
+    }
+    if (cudaFuncSetAttribute(ls_bp_variant<C>(g->bp_minb), cudaFuncAttributeMaxDynamicSharedMemorySize, g->bp_smem) != cudaSuccess) return -1;
+    cudaFuncSetAttribute(ls_bp_variant<C>(g->bp_minb), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_init_kernel<C>, 32, 0);
     g->init = sm_count * (nb > 0 ? nb : 1);
@@ -1386,7 +1431,7 @@ template <class C> int ls_setup_fn(int sm_count, LsGrids* g) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_jac_variant<C>(g->jac_pc, g->jac_minb), 128, 0);
     g->jac = sm_count * (nb > 0 ? nb : 1);
     g->occ_jac = nb;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_bp_kernel<C, LS_BP_WARPS>, 32 * LS_BP_WARPS, g->bp_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_bp_variant<C>(g->bp_minb), 32 * LS_BP_WARPS, g->bp_smem);
     if (nb < 1) return -2;
     g->bp = sm_count * nb;
     g->occ_bp = nb;
@@ -1403,7 +1448,8 @@ template <class C> void ls_launch_fn(int phase, const LsGrids& g, cudaStream_t s
     switch (phase) {
         case LS_PHASE_INIT: ls_init_kernel<C><<<g.init, 32, 0, st>>>(P, B, c, lc); break;
         case LS_PHASE_JAC: ls_jac_variant<C>(g.jac_pc, g.jac_minb)<<<g.jac, 128, 0, st>>>(P, lc, cur); break;
-        case LS_PHASE_BP: ls_bp_kernel<C, LS_BP_WARPS><<<g.bp, 32 * LS_BP_WARPS, g.bp_smem, st>>>(P, c, lc, cur); break;
+        case LS_PHASE_BP: ls_bp_variant<C>(g.bp_minb)<<<g.bp, 32 * LS_BP_WARPS, g.bp_smem, st>>>(P, c, lc, cur); break;
+        case LS_PHASE_BP_SQRT: ls_bp_sqrt_kernel<C><<<g.accept, 64, 0, st>>>(P, c, lc, cur); break;
         case LS_PHASE_TRIAL: ls_trial_variant<C>(g.trial_minb, false)<<<g.trial, 128, 0, st>>>(P, B, c, lc, cur, grp); break;
         case LS_PHASE_TRIAL_ALL: ls_trial_variant<C>(g.trial_minb, true)<<<g.trial, 128, 0, st>>>(P, B, c, lc, cur, 0); break;
         case LS_PHASE_ACCEPT: ls_accept_kernel<C><<<g.accept, 64, 0, st>>>(P, B, c, lc, cur); break;

@@ -1,0 +1,450 @@
+// Square-root backward pass of the lockstep engine (backward_pass.jl:87-192, objective.jl:70-94,
+// augmented_lagrangian_methods.jl:231-276): the cost-to-go and the action-value Hessians are carried as
+// upper-triangular factors, updated with QR "up-dates" (chol_plus) and rank-one down-dates (chol_minus).
+//
+// One THREAD per problem: the factor updates are chains of small Householder reflections with data-dependent
+// branches (cond() by one-sided Jacobi, PosDefException exits), i.e. serial per problem, and the path exists
+// for ill-conditioned small systems (BASELINE config 5: n <= 5), not for throughput.  All matrices are
+// column-major thread-local arrays of compile-time size; every loop follows the order of the CPU restatement
+// so the results are bit-identical to it.
+#pragma once
+#include "engine.cuh"
+
+namespace tob {
+
+template <class C>
+struct SqrtBp {
+    static constexpr int n = C::n, m = C::m, nq = C::nq, mq = C::mq, nz = C::n + C::m;
+    static constexpr int PMAX = 32;                       // constraint rows per knot supported by this path
+    static constexpr int RMAX = n + ((n > PMAX) ? n : PMAX);  // rows of the tallest stacked matrix
+
+    // cholesky(A).U, dot-product (left-looking) form; false = not positive definite
+    template <int D>
+    static __device__ bool chol_upper(const double* A, double* U) {
+        for (int j = 0; j < D; j++) {
+            for (int i = 0; i < j; i++) {
+                double acc = 0.0;
+                for (int l = 0; l < i; l++) acc = fma(U[i * D + l], U[j * D + l], acc);
+                U[j * D + i] = (A[j * D + i] - acc) / U[i * D + i];
+            }
+            double acc = 0.0;
+            for (int l = 0; l < j; l++) acc = fma(U[j * D + l], U[j * D + l], acc);
+            const double dd = A[j * D + j] - acc;
+            if (!(dd > 0.0)) return false;
+            U[j * D + j] = sqrt(dd);
+            for (int i = j + 1; i < D; i++) U[j * D + i] = 0.0;
+        }
+        return true;
+    }
+    template <int D>
+    static __device__ bool chol_upper_inplace(double* A) {
+        double U[D * D];
+        for (int e = 0; e < D * D; e++) U[e] = 0.0;
+        if (!chol_upper<D>(A, U)) return false;
+        for (int e = 0; e < D * D; e++) A[e] = U[e];
+        return true;
+    }
+
+    // Householder QR of the rows×D matrix P (column-major, leading dimension `rows`), in place: R ends up in the
+    // top D×D block (LAPACK dgeqr2 / dlarfg; R may have negative diagonal entries)
+    template <int D>
+    static __device__ void qr_R(double* P, int rows) {
+        for (int j = 0; j < D && j < rows; j++) {
+            const double alpha = P[j * rows + j];
+            double xn2 = 0.0;
+            for (int i = j + 1; i < rows; i++) xn2 = fma(P[j * rows + i], P[j * rows + i], xn2);
+            double tau = 0.0;
+            if (xn2 != 0.0) {
+                const double xnorm = sqrt(xn2);
+                const double beta = -copysign(sqrt(alpha * alpha + xnorm * xnorm), alpha);
+                tau = (beta - alpha) / beta;
+                const double sc = 1.0 / (alpha - beta);
+                for (int i = j + 1; i < rows; i++) P[j * rows + i] = P[j * rows + i] * sc;
+                P[j * rows + j] = beta;
+            }
+            if (tau != 0.0) {
+                for (int c = j + 1; c < D; c++) {
+                    double w = P[c * rows + j];
+                    for (int i = j + 1; i < rows; i++) w = fma(P[j * rows + i], P[c * rows + i], w);
+                    const double tw = tau * w;
+                    P[c * rows + j] = P[c * rows + j] - tw;
+                    for (int i = j + 1; i < rows; i++) P[c * rows + i] = fma(-tw, P[j * rows + i], P[c * rows + i]);
+                }
+            }
+        }
+    }
+    // R = qr([A; B]).R with A: D×D (upper factor, full storage), B: nb×D (leading dimension nb).  `Pbuf`: (D+nb)*D doubles
+    template <int D>
+    static __device__ void chol_plus(const double* A, const double* Bm, int nb, double* Rout, double* Pbuf) {
+        const int rows = D + nb;
+        for (int j = 0; j < D; j++) {
+            for (int i = 0; i < D; i++) Pbuf[j * rows + i] = A[j * D + i];
+            for (int i = 0; i < nb; i++) Pbuf[j * rows + D + i] = Bm[j * nb + i];
+        }
+        qr_R<D>(Pbuf, rows);
+        for (int j = 0; j < D; j++)
+            for (int i = 0; i < D; i++) Rout[j * D + i] = (i <= j) ? Pbuf[j * rows + i] : 0.0;
+    }
+    // lowrankdowndate!(Cholesky(U,:U), v); false on PosDefException
+    template <int D>
+    static __device__ bool lowrank_downdate(double* U, double* v) {
+        for (int i = 0; i < D; i++) {
+            const double Aii = U[i * D + i];
+            const double s = v[i] / Aii;
+            const double s2 = s * s;
+            if (s2 > 1.0) return false;
+            const double c = sqrt(1.0 - s2);
+            U[i * D + i] = c * Aii;
+            for (int j = i + 1; j < D; j++) {
+                const double vj = v[j];
+                const double Aij = (U[j * D + i] - s * vj) / c;
+                U[j * D + i] = Aij;
+                v[j] = -s * Aij + c * vj;
+            }
+        }
+        return true;
+    }
+    // cond(A): ratio of the extreme singular values by one-sided Jacobi (fixed sweep order)
+    template <int D>
+    static __device__ double cond2(const double* Ain) {
+        double A[D * D];
+        for (int e = 0; e < D * D; e++) A[e] = Ain[e];
+        for (int sweep = 0; sweep < 60; sweep++) {
+            double off = 0.0;
+            for (int p = 0; p < D - 1; p++)
+                for (int q = p + 1; q < D; q++) {
+                    double a = 0, b = 0, c = 0;
+                    for (int i = 0; i < D; i++) {
+                        a = fma(A[p * D + i], A[p * D + i], a);
+                        b = fma(A[q * D + i], A[q * D + i], b);
+                        c = fma(A[p * D + i], A[q * D + i], c);
+                    }
+                    if (c == 0.0) continue;
+                    off = dmax(off, fabs(c) / sqrt(a * b));
+                    const double zeta = (b - a) / (2.0 * c);
+                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                    for (int i = 0; i < D; i++) {
+                        const double ap = A[p * D + i], aq = A[q * D + i];
+                        A[p * D + i] = cs * ap - sn * aq;
+                        A[q * D + i] = sn * ap + cs * aq;
+                    }
+                }
+            if (off < 1e-15) break;
+        }
+        double smax = 0.0, smin = __longlong_as_double(0x7ff0000000000000LL);
+        for (int j = 0; j < D; j++) {
+            double a = 0;
+            for (int i = 0; i < D; i++) a = fma(A[j * D + i], A[j * D + i], a);
+            const double sv = sqrt(a);
+            smax = dmax(smax, sv);
+            smin = dmin(smin, sv);
+        }
+        return smax / smin;
+    }
+    // X = U \ B and X = U' \ B for an upper-triangular D×D U, nrhs right-hand sides (column-major, ld D)
+    template <int D>
+    static __device__ void solve_upper(const double* U, const double* Bin, int nrhs, double* X) {
+        for (int c = 0; c < nrhs; c++)
+            for (int i = D - 1; i >= 0; i--) {
+                double acc = 0.0;
+                for (int l = i + 1; l < D; l++) acc = fma(U[l * D + i], X[c * D + l], acc);
+                X[c * D + i] = (Bin[c * D + i] - acc) / U[i * D + i];
+            }
+    }
+    template <int D>
+    static __device__ void solve_upper_t(const double* U, const double* Bin, int nrhs, double* X) {
+        for (int c = 0; c < nrhs; c++)
+            for (int i = 0; i < D; i++) {
+                double acc = 0.0;
+                for (int l = 0; l < i; l++) acc = fma(U[i * D + l], X[c * D + l], acc);
+                X[c * D + i] = (Bin[c * D + i] - acc) / U[i * D + i];
+            }
+    }
+    // C = A'B (A: ra×ca, B: ra×cb) and C = A B (A: ra×ca, B: ca×cb), column-major
+    static __device__ void mul_AtB(const double* A, int ra, int ca, const double* Bm, int cb, double* Cm) {
+        for (int j = 0; j < cb; j++)
+            for (int i = 0; i < ca; i++) {
+                double acc = 0.0;
+                for (int l = 0; l < ra; l++) acc = fma(A[i * ra + l], Bm[j * ra + l], acc);
+                Cm[j * ca + i] = acc;
+            }
+    }
+    static __device__ void mul_AB(const double* A, int ra, int ca, const double* Bm, int cb, double* Cm) {
+        for (int j = 0; j < cb; j++)
+            for (int i = 0; i < ra; i++) {
+                double acc = 0.0;
+                for (int l = 0; l < ca; l++) acc = fma(A[l * ra + i], Bm[j * ca + l], acc);
+                Cm[j * ra + i] = acc;
+            }
+    }
+
+    // cost expansion of knot k in square-root form -> E = [x(n) u(m) xx(n*n) uu(m*m) ux(m*n)] (the QST layout).
+    // false: a stage Hessian is not positive definite (objective.jl:76-93)
+    static __device__ bool expansion(const DevProblem& P, bool al_on, int k, const double* x, const double* u,
+                                     const double* lam, const double* mu, double* E, double* Pbuf) {
+        const int N = P.N;
+        const bool term = (k == N - 1);
+        double* Ex = E;
+        double* Eu = E + n;
+        double* Exx = E + n + m;
+        double* Euu = Exx + n * n;
+        double* Eux = Euu + m * m;
+        for (int e = 0; e < C::QS; e++) E[e] = 0.0;
+        if (!term) {
+            // src/cost.jl:183-192 / minimum_time.jl:161-191
+            double Qx[nq], Qu[mq];
+            for (int i = 0; i < nq; i++) {
+                double a = 0.0, b = 0.0;
+                for (int j = 0; j < nq; j++) a = fma(P.Q[j * nq + i], x[j], a);
+                for (int j = 0; j < mq; j++) b = fma(P.H[i * mq + j], u[j], b);
+                Qx[i] = (a + P.q[i]) + b;
+            }
+            for (int i = 0; i < mq; i++) {
+                double a = 0.0, b = 0.0;
+                for (int j = 0; j < mq; j++) a = fma(P.R[j * mq + i], u[j], a);
+                for (int j = 0; j < nq; j++) b = fma(P.H[j * mq + i], x[j], b);
+                Qu[i] = (a + P.r[i]) + b;
+            }
+            double dt = P.dt, tau = 0.0;
+            if (C::MT) { tau = u[m - 1]; dt = tau * tau; }
+            for (int i = 0; i < nq; i++) Ex[i] = Qx[i] * dt;
+            for (int i = 0; i < mq; i++) Eu[i] = Qu[i] * dt;
+            for (int j = 0; j < nq; j++) for (int i = 0; i < nq; i++) Exx[j * n + i] = P.Q[j * nq + i] * dt;
+            for (int j = 0; j < mq; j++) for (int i = 0; i < mq; i++) Euu[j * m + i] = P.R[j * mq + i] * dt;
+            for (int j = 0; j < nq; j++) for (int i = 0; i < mq; i++) Eux[j * m + i] = P.H[j * mq + i] * dt;
+            if (C::MT) {
+                const double l1 = quad_stage<C>(P, x, u);
+                Eu[m - 1] = tau * (2.0 * l1 + P.R_mt);
+                for (int i = 0; i < mq; i++) {
+                    const double t = (2.0 * tau) * Qu[i];
+                    Euu[(m - 1) * m + i] = t;
+                    Euu[i * m + (m - 1)] = t;
+                }
+                Euu[(m - 1) * m + (m - 1)] = 2.0 * l1 + P.R_mt;
+                for (int i = 0; i < nq; i++) Eux[i * m + (m - 1)] = (2.0 * tau) * Qx[i];
+                Ex[n - 1] = P.R_mt * x[n - 1];
+                Exx[(n - 1) * n + (n - 1)] = P.R_mt;
+            }
+            if (!chol_upper_inplace<n>(Exx)) return false;
+            if (!chol_upper_inplace<m>(Euu)) return false;
+        } else {
+            // src/cost.jl:194-198 / minimum_time.jl:193-204
+            for (int j = 0; j < nq; j++) for (int i = 0; i < nq; i++) Exx[j * n + i] = P.Qf[j * nq + i];
+            for (int i = 0; i < nq; i++) {
+                double a = 0.0;
+                for (int j = 0; j < nq; j++) a = fma(P.Qf[j * nq + i], x[j], a);
+                Ex[i] = a + P.qf[i];
+            }
+            if (C::MT) {
+                Exx[(n - 1) * n + (n - 1)] = P.R_mt;
+                Ex[n - 1] = P.R_mt * x[n - 1];
+            }
+            if (!chol_upper_inplace<n>(Exx)) return false;
+        }
+        if (!al_on) return true;
+        const int rb = P.knot_row_begin[k], pk = P.knot_row_count[k];
+        if (pk == 0) return true;
+        // augmented_lagrangian_methods.jl:231-276 (no ux term)
+        double G[PMAX * nz], Bx[PMAX * n], Bu[PMAX * m], g[PMAX];
+        const int cols = term ? n : nz;
+        for (int r_ = 0; r_ < pk; r_++) {
+            const DevRow r = P.rows[rb + r_];
+            const double c = row_value<C>(r, x, u);
+            const bool act = r.eq ? true : ((c >= 0.0) || (lam[r_] > 0.0));
+            const double im = act ? mu[r_] : 0.0;
+            for (int jj = 0; jj < nz; jj++) G[r_ * nz + jj] = (jj < cols) ? row_jac<C>(r, x, jj) : 0.0;
+            g[r_] = im * c + lam[r_];
+            const double sq = act ? sqrt(mu[r_]) : 0.0;
+            for (int jj = 0; jj < n; jj++) Bx[jj * pk + r_] = sq * G[r_ * nz + jj];
+            if (!term) for (int jj = 0; jj < m; jj++) Bu[jj * pk + r_] = sq * G[r_ * nz + n + jj];
+        }
+        {
+            double R[n * n];
+            chol_plus<n>(Exx, Bx, pk, R, Pbuf);
+            for (int e = 0; e < n * n; e++) Exx[e] = R[e];
+        }
+        if (!term) {
+            double R[m * m];
+            chol_plus<m>(Euu, Bu, pk, R, Pbuf);
+            for (int e = 0; e < m * m; e++) Euu[e] = R[e];
+        }
+        for (int i = 0; i < n; i++) {
+            double acc = 0.0;
+            for (int r_ = 0; r_ < pk; r_++) acc = fma(G[r_ * nz + i], g[r_], acc);
+            Ex[i] += acc;
+        }
+        if (!term)
+            for (int i = 0; i < m; i++) {
+                double acc = 0.0;
+                for (int r_ = 0; r_ < pk; r_++) acc = fma(G[r_ * nz + n + i], g[r_], acc);
+                Eu[i] += acc;
+            }
+        return true;
+    }
+
+    // The square-root backward pass of one problem.  Returns 0 = ok, 1 = restart loop diverged (TO_STATUS_REG_DIVERGED),
+    // 2 = PosDefException (TO_STATUS_NOT_PD_SQRT).
+    static __device__ int run(const DevProblem& P, bool al_on, const TOiLQROptions& io, double* ws, const WsLayout& L,
+                              double& rho, double& drho, double& dV0, double& dV1) {
+        const int N = P.N;
+        double Pbuf[RMAX * ((n > m) ? n : m)];
+        double Sxx[n * n], Sx[n];
+        // cost_expansion_sqrt! of every knot first (ilqr_methods.jl:55-62): the Q trajectory lives in global memory and
+        // is updated IN PLACE by the recursion, which reproduces the reference's restart behaviour as is
+        double* qst = ws + L.QST;
+        {
+            double x[n], u[m], E[C::QS];
+            for (int k = 0; k < N; k++) {
+                for (int i = 0; i < n; i++) x[i] = ws[L.X + (size_t)k * n + i];
+                for (int i = 0; i < m; i++) u[i] = (k < N - 1) ? ws[L.U + (size_t)k * m + i] : 0.0;
+                const int lo = P.knot_lam_off[k];
+                if (P.knot_row_count[k] > PMAX && al_on) return 2;
+                if (!expansion(P, al_on, k, x, u, ws + L.LAM + lo, ws + L.MU + lo, E, Pbuf)) return 2;
+                if (k < N - 1) {
+                    for (int e = 0; e < C::QS; e++) qst[(size_t)k * C::QS + e] = E[e];
+                } else {
+                    for (int e = 0; e < n * n; e++) Sxx[e] = E[n + m + e];
+                    for (int i = 0; i < n; i++) Sx[i] = E[i];
+                }
+            }
+        }
+        // the terminal factor is re-used by every restart
+        double SxxN[n * n], SxN[n];
+        for (int e = 0; e < n * n; e++) SxxN[e] = Sxx[e];
+        for (int i = 0; i < n; i++) SxN[i] = Sx[i];
+        dV0 = 0.0;
+        dV1 = 0.0;
+        int k = N - 2;
+        while (k >= 0) {
+            double A[n * n], Bm[n * m];
+            {
+                const double* ab = ws + L.Z + (size_t)k * C::ZA;
+                for (int jj = 0; jj < n; jj++) for (int i = 0; i < n; i++) A[jj * n + i] = ab[i * C::LDZ + jj];
+                for (int jj = 0; jj < m; jj++) for (int i = 0; i < n; i++) Bm[jj * n + i] = ab[i * C::LDZ + n + jj];
+            }
+            double* Q = qst + (size_t)k * C::QS;
+            double* Qx = Q;
+            double* Qu = Q + n;
+            double* Qxx = Q + n + m;
+            double* Quu = Qxx + n * n;
+            double* Qux = Quu + m * m;
+            double v[n], vu[m], tx[n * n], tu[n * m], Mux[m * n];
+            mul_AtB(A, n, n, Sx, 1, v);
+            for (int i = 0; i < n; i++) Qx[i] += v[i];
+            mul_AtB(Bm, n, m, Sx, 1, vu);
+            for (int i = 0; i < m; i++) Qu[i] += vu[i];
+            mul_AB(Sxx, n, n, A, n, tx);
+            mul_AB(Sxx, n, n, Bm, m, tu);
+            {
+                double R[n * n];
+                chol_plus<n>(Qxx, tx, n, R, Pbuf);
+                for (int e = 0; e < n * n; e++) Qxx[e] = R[e];
+            }
+            {
+                double R[m * m];
+                chol_plus<m>(Quu, tu, n, R, Pbuf);
+                for (int e = 0; e < m * m; e++) Quu[e] = R[e];
+            }
+            mul_AtB(tu, n, m, tx, n, Mux);
+            for (int e = 0; e < m * n; e++) Qux[e] += Mux[e];
+            double eye[m * m], Quu_reg[m * m];
+            for (int e = 0; e < m * m; e++) eye[e] = 0.0;
+            const double sr = sqrt(rho);
+            for (int i = 0; i < m; i++) eye[i * m + i] = sr * 1.0;
+            chol_plus<m>(Quu, eye, m, Quu_reg, Pbuf);
+            if (cond2<m>(Quu_reg) > 1e8) {
+                if (!isfinite(rho)) return 1;
+                const double f = io.bp_reg_increase_factor;  // regularization_update!(:increase)
+                drho = dmax(drho * f, f);
+                rho = dmax(rho * drho, io.bp_reg_min);
+                k = N - 2;
+                for (int e = 0; e < n * n; e++) Sxx[e] = SxxN[e];
+                for (int i = 0; i < n; i++) Sx[i] = SxN[i];
+                dV0 = 0.0;
+                dV1 = 0.0;
+                continue;
+            }
+            // K = -Quu_reg \ (Quu_reg' \ Qux) ; d likewise
+            double t1[m * n], Kk[m * n], dk[m], t1d[m];
+            solve_upper_t<m>(Quu_reg, Qux, n, t1);
+            solve_upper<m>(Quu_reg, t1, n, Kk);
+            for (int e = 0; e < m * n; e++) Kk[e] = -Kk[e];
+            solve_upper_t<m>(Quu_reg, Qu, 1, t1d);
+            solve_upper<m>(Quu_reg, t1d, 1, dk);
+            for (int i = 0; i < m; i++) dk[i] = -dk[i];
+            {
+                double* kd = ws + L.KD + (size_t)k * C::KDS;
+                for (int e = 0; e < m * n; e++) kd[e] = Kk[e];
+                for (int i = 0; i < m; i++) kd[m * n + i] = dk[i];
+            }
+            // S.x = Q.x + (K'Quu')(Quu d) + K'Qu + Qux'd
+            double KQt[n * m], Qd[m], v1[n], v2[n], v3[n];
+            for (int jj = 0; jj < m; jj++)
+                for (int i = 0; i < n; i++) {
+                    double acc = 0.0;
+                    for (int l = 0; l < m; l++) acc = fma(Kk[i * m + l], Quu[l * m + jj], acc);
+                    KQt[jj * n + i] = acc;
+                }
+            mul_AB(Quu, m, m, dk, 1, Qd);
+            mul_AB(KQt, n, m, Qd, 1, v1);
+            mul_AtB(Kk, m, n, Qu, 1, v2);
+            mul_AtB(Qux, m, n, dk, 1, v3);
+            double Sxk[n];
+            for (int i = 0; i < n; i++) Sxk[i] = ((Qx[i] + v1[i]) + v2[i]) + v3[i];
+            // tmp1 = (Q.xx') \ Q.ux'  (n×m) ; tmp2 = chol_minus(Q.uu, tmp1)
+            double uxT[n * m], tmp1[n * m];
+            for (int jj = 0; jj < m; jj++) for (int i = 0; i < n; i++) uxT[jj * n + i] = Qux[i * m + jj];
+            solve_upper_t<n>(Qxx, uxT, m, tmp1);
+            double U2[m * m];
+            for (int e = 0; e < m * m; e++) U2[e] = Quu[e];
+            for (int i = 0; i < n; i++) {
+                double rowv[m];
+                for (int jj = 0; jj < m; jj++) rowv[jj] = tmp1[jj * n + i];
+                if (!lowrank_downdate<m>(U2, rowv)) return 2;
+            }
+            // S.xx = chol_plus(Q.xx + tmp1*K, tmp2*K)
+            double top[n * n], bot[m * n];
+            mul_AB(tmp1, n, m, Kk, n, top);
+            for (int e = 0; e < n * n; e++) top[e] = Qxx[e] + top[e];
+            mul_AB(U2, m, m, Kk, n, bot);
+            chol_plus<n>(top, bot, m, Sxx, Pbuf);
+            for (int i = 0; i < n; i++) Sx[i] = Sxk[i];
+            {
+                double a = 0.0;
+                for (int l = 0; l < m; l++) a = fma(dk[l], Qu[l], a);
+                dV0 += a;
+                double b = 0.0;
+                for (int l = 0; l < m; l++) b = fma(Qd[l], Qd[l], b);
+                dV1 += 0.5 * b;
+            }
+            k--;
+        }
+        {
+            const double f = io.bp_reg_increase_factor;  // regularization_update!(:decrease)
+            drho = dmin(drho / f, 1.0 / f);
+            rho = rho * drho * ((rho * drho > io.bp_reg_min) ? 1.0 : 0.0);
+        }
+        return 0;
+    }
+};
+
+// thread per problem
+template <class C>
+__global__ void __launch_bounds__(64) ls_bp_sqrt_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
+    const unsigned int na = lc.counts[cur];
+    const WsLayout L = ws_layout<C>(P.N, P.Ptot, false);
+    const bool al_on = (ctl.mode == 1);
+    for (unsigned int a = blockIdx.x * blockDim.x + threadIdx.x; a < na; a += gridDim.x * blockDim.x) {
+        const int b = lc.list[cur][a];
+        LsState* st = &lc.st[b];
+        TOiLQROptions io = ctl.o.opts_uncon;
+        double rho = st->rho, drho = st->drho, dV0 = 0.0, dV1 = 0.0;
+        const int rc = SqrtBp<C>::run(P, al_on, io, lc.ws + (size_t)b * lc.ws_stride, L, rho, drho, dV0, dV1);
+        st->rho = rho; st->drho = drho; st->dV0 = dV0; st->dV1 = dV1;
+        st->winner = -1;
+        st->bp_fail = rc;
+    }
+}
+
+}  // namespace tob
