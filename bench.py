@@ -34,6 +34,17 @@ sys.path.insert(0, ROOT)
 QUAD = dict(n=13, m=4, N=101, p_stage=4, p_term=18, c_f=190.0)
 
 
+def algorithmic_bp():
+    """FLOPs and HBM bytes of ONE backward pass of one QUAD problem = one problem's share of one launch of the
+    dominant kernel ls_bp_kernel (SURVEY.md §8d F_bp; bytes: A,B,X,U,lambda,mu read once, K,d written once)."""
+    n, m, N, p, pN = QUAD["n"], QUAD["m"], QUAD["N"], QUAD["p_stage"], QUAD["p_term"]
+    F_bp = (N - 1) * (4 * n**3 + 6 * n * n * m + 2 * n * m * m + 2 * n * n + 2 * n * m + m**3 / 3 + 4 * m**3 / 3 + 2 * m * m * n
+                      + 2 * m * m + 6 * n * n * m + 4 * n * m * m + 6 * n * m + 5 * n * n + 3 * n + 2 * m * m + 4 * m)
+    sum_p = (N - 1) * p + pN
+    nbytes = 8 * ((N - 1) * n * (n + m) + N * n + (N - 1) * m + (N - 1) * (m * n + m) + 2 * sum_p)
+    return F_bp, nbytes
+
+
 def algorithmic_per_iter(L):
     """FLOPs and HBM bytes of one iLQR iteration of one QUAD problem (FMA = 2)."""
     n, m, N, p, pN, cf = QUAD["n"], QUAD["m"], QUAD["N"], QUAD["p_stage"], QUAD["p_term"], QUAD["c_f"]
@@ -124,7 +135,7 @@ def run_reference(args, rank, world):
     from trajopt_b200 import problems
     prob, opts = make_problem()
     cores = host_cores()
-    sample = args.cpu_sample or max(cores, 4 * cores)
+    sample = args.cpu_sample or 24 * cores  # ~8 s of host work per step on the 16-core GPU box
     x0 = problems.batch_x0("quadrotor", sample, offset=0)
     for _ in range(args.warmup):
         oracle_py.solve(prob, opts, x0=x0[:cores], B=cores, inner_cap=0, outer_cap=0, threads=cores)
@@ -244,6 +255,11 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    lockstep = os.environ.get("TRAJOPT_B200_ENGINE", "lockstep")[0] not in "p0"
+    if lockstep:
+        lib.to_debug_phase_timing(bs.h, 1)  # one CUDA event per phase kernel on the engine's stream
+    phase_ms = np.zeros(5)
+    ticks_total = 0
     barrier()
     t_wall0 = time.perf_counter()
     step_ms, kernel_ms = [], []
@@ -251,6 +267,13 @@ def main():
         ms = resident_step()
         step_ms.append(ms)
         kernel_ms.append(bs.kernel_ms())
+        if lockstep:
+            pm = (C.c_double * 5)()
+            lib.to_debug_phase_ms(bs.h, pm)
+            phase_ms += np.array(list(pm))
+            tk = C.c_int32()
+            lib.to_debug_ticks(bs.h, C.byref(tk))
+            ticks_total += tk.value
         log("timed step: %.1f ms" % ms)
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -279,9 +302,9 @@ def main():
         ms_per_step = total_ms / args.steps
         value = world * B / (ms_per_step * 1e-3)
         iters_per_s = steps_all / (ms_per_step * 1e-3)
-        # roofline of the dominant (only) kernel, per launch, this rank
-        iters_rank = float(res["steps"].sum())
-        L = float(trials.value) / max(1.0, iters_rank)
+        # ---- roofline ------------------------------------------------------------------------------------
+        iters_rank = float(res["steps"].sum())          # iLQR iterations (= backward passes) of this rank, last step
+        L = float(trials.value) / max(1.0, iters_rank)  # sequential-equivalent line-search trials per iteration
         f_it, b_it = algorithmic_per_iter(L)
         kms = float(np.mean(kernel_ms))
         peaks = {}
@@ -290,20 +313,47 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        ach_gbs = iters_rank * b_it / (kms * 1e-3) / 1e9
+        hbm_src = "measured copy bandwidth (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         fp64 = C.c_double()
         lib.to_measure_fp64_peak(local_rank, C.byref(fp64))
-        ach_tf = iters_rank * f_it / (kms * 1e-3) / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch_at_bench_batch")
-            except Exception:
-                traffic = None
+        prof = {}
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
+        except Exception:
+            pass
         h2d = x0_h.numel() * 8 + U0_h.numel() * 8
         d2h = X_h.numel() * 8 + U_h.numel() * 8 + dts_h.numel() * 8 + res_h.numel()
+        whole = {"achieved_tflops": iters_rank * f_it / (kms * 1e-3) / 1e12, "achieved_gbs": iters_rank * b_it / (kms * 1e-3) / 1e9,
+                 "algorithmic_flops_per_iter": f_it, "algorithmic_bytes_per_iter": b_it, "solve_ms": kms}
+        if lockstep and ticks_total > 0 and phase_ms[1] > 0:
+            # dominant kernel: the backward pass (one launch per tick, one pass per live problem per launch)
+            F_bp, B_bp = algorithmic_bp()
+            launches_bp = ticks_total                       # over the timed steps
+            passes = iters_rank * args.steps                # every step solves the same batch: same iteration counts
+            bp_ms = float(phase_ms[1])
+            ach_tf = passes * F_bp / (bp_ms * 1e-3) / 1e12
+            ach_gbs = passes * B_bp / (bp_ms * 1e-3) / 1e9
+            traffic_pp = prof.get("ls_bp_kernel_dram_bytes_per_problem_pass")
+            roofline = {
+                "bound": "fp64", "achieved": ach_tf, "peak": fp64.value, "unit": "TFLOP/s", "frac": ach_tf / fp64.value if fp64.value > 0 else None,
+                "traffic": (traffic_pp * passes / launches_bp) if traffic_pp else None,
+                "kernel": "tob::ls_bp_kernel<Cfg<4,0,false,false,2>,4,3> (backward pass; %.0f%% of the device time of a step)" % (
+                    100.0 * bp_ms / max(1e-9, float(phase_ms.sum()))),
+                "peak_source": "measured register-resident DFMA probe (to_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; "
+                               "tensor cores do not apply (13x13 FP64 contractions)",
+                "launches": int(launches_bp), "avg_launch_ms": bp_ms / launches_bp,
+                "algorithmic_flops_per_launch": passes * F_bp / launches_bp, "algorithmic_bytes_per_launch": passes * B_bp / launches_bp,
+                "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": hbm_src},
+                "phase_ms_per_step": {k: float(v) / args.steps for k, v in zip(("jac", "bp", "trial", "accept", "outer"), phase_ms)},
+                "whole_solve": whole,
+            }
+        else:
+            roofline = {"bound": "fp64", "achieved": whole["achieved_tflops"], "peak": fp64.value, "unit": "TFLOP/s",
+                        "frac": whole["achieved_tflops"] / fp64.value if fp64.value > 0 else None, "traffic": None,
+                        "kernel": "tob::solve_kernel<Cfg<4,0,false,false,2>> (persistent engine: the whole solve is one kernel)",
+                        "peak_source": "measured DFMA probe (to_measure_fp64_peak)",
+                        "hbm": {"achieved": whole["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": whole["achieved_gbs"] / hbm_peak,
+                                "peak_source": hbm_src}, "whole_solve": whole}
         out = {
             "metric": "ALTRO solves/s (batched quadrotor N=101)", "value": value, "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -312,17 +362,13 @@ def main():
             "config": {"workload": "quadrotor ALTRO (AL phase of benchmark/quadrotor_benchmarks.jl, PN off), n=13 m=4 N=101 rk3, "
                                    "u>=0 + terminal box, per-problem random x0 (SURVEY 8d item 3)",
                        "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d (batch sharded, no solve-path collective)" % world,
-                       "l2_policy": "inputs (x0+U0 = %.0f MB per GPU) and the %.0f MB workspace exceed the 126 MB L2" % (
-                           (x0_h.numel() + U0_h.numel()) * 8 / 1e6, 0.0),
-                       "mean_iters_per_solve": steps_all / (world * B), "mean_linesearch_trials": L},
+                       "engine": "lockstep" if lockstep else "persistent",
+                       "mean_iters_per_solve": steps_all / (world * B), "mean_linesearch_trials": L,
+                       "ticks_per_step": ticks_total / max(1, args.steps)},
             "e2e": {"value": world * B / (e2e_mean * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_mean, "timing": "CUDA events on the engine stream around H2D(pinned)+solve+D2H"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": traffic, "peak_source": hbm_src, "kernel": "tob::solve_kernel<Cfg<4,0,false,false,2>>",
-                         "algorithmic_bytes_per_iter": b_it, "kernel_ms": kms,
-                         "fp64": {"achieved_tflops": ach_tf, "peak_tflops": fp64.value, "frac": ach_tf / fp64.value if fp64.value > 0 else None,
-                                  "algorithmic_flops_per_iter": f_it, "peak_source": "measured DFMA probe (to_measure_fp64_peak)"}},
+            "roofline": roofline,
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
             "status_histogram": {str(int(k)): int(v) for k, v in zip(*np.unique(res["status"], return_counts=True))},
@@ -330,14 +376,15 @@ def main():
         ws = C.c_uint64()
         g, sm = C.c_int32(), C.c_int32()
         if lib.to_debug_grid(bs.h, 0, C.byref(g), C.byref(sm), C.byref(ws)) == 0:
-            out["config"]["l2_policy"] = "inputs (x0+U0 = %.0f MB per GPU) and the per-warp workspaces (%d warps x %.2f MB = %.0f MB) exceed the 126 MB L2" % (
-                (x0_h.numel() + U0_h.numel()) * 8 / 1e6, g.value, ws.value * 8 / 1e6, g.value * ws.value * 8 / 1e6)
-            out["config"]["grid_warps"] = g.value
+            nws = B if lockstep else g.value
+            out["config"]["l2_policy"] = ("inputs (x0+U0 = %.0f MB per GPU) and the solver workspaces (%d x %.2f MB = %.0f MB) exceed the 126 MB L2; "
+                                          "no flush needed between steps" % ((x0_h.numel() + U0_h.numel()) * 8 / 1e6, nws, ws.value * 8 / 1e6,
+                                                                           nws * ws.value * 8 / 1e6))
         if not args.no_cpu_baseline and world == 1:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import oracle_py
             cores = host_cores()
-            sample = args.cpu_sample or 6 * cores
+            sample = args.cpu_sample or 48 * cores  # ~10 s of host work on the 16-core GPU box
             log("cpu baseline: %d problems on %d threads" % (sample, cores))
             t0 = time.perf_counter()
             r = oracle_py.solve(prob, opts, x0=x0_np[:sample], B=sample, inner_cap=0, outer_cap=0, threads=cores)

@@ -62,11 +62,47 @@ def _compare(ref, gpu, B, atol_xu=1e-10):
 
 @pytest.mark.parametrize("name", [c for c in CASES if c not in ("escape_altro",)])
 def test_parity_small_batches(to, oracle, name):
+    """every parity case on the default (lockstep) engine, in tail mode (few live problems: all step sizes in one launch)"""
     B = 8
     prob, opts, x0, X0 = CASES[name](B)
     ref = oracle.solve(prob, opts, x0=x0, X0=X0, B=B, inner_cap=2048, outer_cap=96)
     gpu = _solve_gpu(to, prob, opts, x0, X0, B)
     _compare(ref, gpu, B)
+
+
+@pytest.mark.parametrize("name", ["quad_altro", "quad_regdiv", "cart_altro", "escape_notebook", "park_inf_altro", "pend_mintime",
+                                  "acrobot_sqrt_al"])
+def test_parity_grouped_line_search(to, oracle, name, monkeypatch):
+    """the same engine with tail mode off: step sizes tried 8 at a time with retry lists (the bulk path of large batches)"""
+    monkeypatch.setenv("TRAJOPT_B200_TAIL_THRESHOLD", "0")
+    B = 8
+    prob, opts, x0, X0 = CASES[name](B)
+    ref = oracle.solve(prob, opts, x0=x0, X0=X0, B=B, inner_cap=2048, outer_cap=96)
+    gpu = _solve_gpu(to, prob, opts, x0, X0, B)
+    _compare(ref, gpu, B)
+
+
+@pytest.mark.parametrize("name", ["di_altro", "quad_altro", "quad_regdiv", "cart_ilqr", "escape_notebook", "park_inf_altro", "pend_mintime"])
+def test_parity_persistent_engine(to, oracle, name, monkeypatch):
+    """the second, independent CUDA implementation (one warp-resident kernel per solve, engine.cuh) against the same oracle"""
+    monkeypatch.setenv("TRAJOPT_B200_ENGINE", "persistent")
+    B = 8
+    prob, opts, x0, X0 = CASES[name](B)
+    ref = oracle.solve(prob, opts, x0=x0, X0=X0, B=B, inner_cap=2048, outer_cap=96)
+    gpu = _solve_gpu(to, prob, opts, x0, X0, B)
+    _compare(ref, gpu, B)
+
+
+def test_status_bits_match_the_oracle(to, oracle):
+    """per-problem status instead of exceptions: REG_DIVERGED (problem 6326 of the synthetic quadrotor batch) and
+    NOT_PD_SQRT (square-root + minimum time) are reported identically by oracle and engine"""
+    prob, opts, x0, X0 = CASES["quad_regdiv"](8)
+    gpu = _solve_gpu(to, prob, opts, x0, X0, 8, inner_cap=0, outer_cap=0)
+    assert gpu["results"]["status"][2] == 32 and np.count_nonzero(gpu["results"]["status"]) == 1
+    prob, opts, x0, X0 = CASES["acrobot_sqrt_mintime"](8)
+    gpu = _solve_gpu(to, prob, opts, x0, X0, 8, inner_cap=0, outer_cap=0)
+    ref = oracle.solve(prob, opts, x0=x0, X0=X0, B=8, inner_cap=0, outer_cap=0)
+    assert np.array_equal(gpu["results"]["status"], ref["results"]["status"]) and np.all(gpu["results"]["status"] & 4)
 
 
 def test_parity_car_escape_170_circles(to, oracle):

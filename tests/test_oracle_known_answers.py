@@ -193,3 +193,20 @@ def test_sincos_within_one_ulp(oracle):
         s, c = oracle.sincos(float(x))
         assert abs(s - math.sin(x)) <= np.spacing(abs(math.sin(x))) and abs(c - math.cos(x)) <= np.spacing(abs(math.cos(x)))
     assert all(np.isnan(v) for v in oracle.sincos(float("inf")))
+
+
+def test_oracle_reports_status_instead_of_hanging_or_throwing(oracle):
+    """(a) problem 6326 of the synthetic quadrotor batch: the reference's in-place Q accumulation blows
+    Quu up to NaN and its backward pass would restart forever; the restatement stops with TO_STATUS_REG_DIVERGED once
+    rho is no longer finite.  (b) square-root + minimum time: cost_expansion_sqrt! hits a non-PD stage Hessian
+     -> TO_STATUS_NOT_PD_SQRT, every other problem of the batch unaffected."""
+    from cases import CASES
+    prob, opts, x0, X0 = CASES["quad_regdiv"](4)
+    r = oracle.solve(prob, opts, x0=x0, X0=X0, B=4, inner_cap=0, outer_cap=0)
+    assert r["results"]["status"].tolist() == [0, 0, 32, 0]
+    prob, opts, x0, X0 = CASES["acrobot_sqrt_mintime"](4)
+    r = oracle.solve(prob, opts, x0=x0, X0=X0, B=4, inner_cap=0, outer_cap=0)
+    assert np.all(r["results"]["status"] == 4)
+    prob, opts, x0, X0 = CASES["pend_sqrt_altro"](4)
+    r = oracle.solve(prob, opts, x0=x0, X0=X0, B=4, inner_cap=0, outer_cap=0)
+    assert np.all(r["results"]["status"] == 0) and np.all(r["results"]["c_max"] < 1e-3)

@@ -82,6 +82,8 @@ struct TOSolver {
     int blocks_per_sm_override = 0;
     int engine = 1;              // 0 = warp-persistent kernel (engine.cuh), 1 = lockstep phase kernels (lockstep.cuh)
     int ticks = 0;               // lockstep ticks enqueued by the last solve
+    int phase_timing = 0;        // 1: time every phase kernel of the lockstep engine with CUDA events
+    double phase_ms[5] = {0, 0, 0, 0, 0};  // device ms of the last solve: jac, bp, trial, accept, outer
     unsigned int* h_counts = nullptr;  // pinned ring of active-list sizes read back from the device
     cudaEvent_t ring_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
@@ -328,13 +330,23 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
     unsigned int known_active = (unsigned int)s->B;  // upper bound (the list only shrinks), refreshed LAG ticks late
     // diagnostics: TRAJOPT_B200_TICK_LOG=<file> records one event per tick and writes "tick ms active" lines
     const char* tick_log = getenv("TRAJOPT_B200_TICK_LOG");
-    const bool phase_log = tick_log && getenv("TRAJOPT_B200_TICK_DETAIL");
+    const bool collect = tick_log || s->phase_timing;  // one CUDA event per phase (or per tick) on the solve stream
+    const bool phase_log = (tick_log && getenv("TRAJOPT_B200_TICK_DETAIL")) || s->phase_timing;
     std::vector<cudaEvent_t> tick_ev;
     std::vector<unsigned int> tick_active;
     auto dump_ticks = [&]() {
-        if (!tick_log || tick_ev.size() < 2) return;
+        if (!collect || tick_ev.size() < 2) return;
         cudaStreamSynchronize(st);
-        FILE* f = fopen(tick_log, "a");
+        if (s->phase_timing) {
+            // accumulate per-phase device time of this run: [jac, bp, trial, accept, outer]
+            for (size_t i = 1; i + 4 < tick_ev.size(); i += 5)
+                for (size_t q = 0; q < 5; q++) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, tick_ev[i + q - 1], tick_ev[i + q]);
+                    s->phase_ms[q] += ms;
+                }
+        }
+        FILE* f = tick_log ? fopen(tick_log, "a") : nullptr;
         if (f) {
             const size_t per = phase_log ? 5 : 1;  // events per tick: [jac, bp, trials, accept,] outer
             fprintf(f, "# solve B=%d ticks=%zu%s\n", s->B, (tick_ev.size() - 1) / per, phase_log ? " columns: tick jac bp trial accept outer active" : "");
@@ -352,7 +364,7 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
         }
         for (auto e : tick_ev) cudaEventDestroy(e);
     };
-    if (tick_log) {
+    if (collect) {
         cudaEvent_t e;
         cudaEventCreate(&e);
         cudaEventRecord(e, st);
@@ -390,7 +402,7 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
         const int slot = (int)(t % RING);
         CK_RET(s, cudaMemcpyAsync(&s->h_counts[slot], v.lc.counts + (cur ^ 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         CK_RET(s, cudaEventRecord(s->ring_ev[slot], st));
-        if (tick_log) {
+        if (collect) {
             cudaEvent_t e;
             cudaEventCreate(&e);
             cudaEventRecord(e, st);
@@ -400,7 +412,7 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
             const int old = (int)((t - LAG) % RING);
             CK_RET(s, cudaEventSynchronize(s->ring_ev[old]));
             known_active = s->h_counts[old];
-            if (tick_log) tick_active.push_back(known_active);
+            if (collect) tick_active.push_back(known_active);
             if (known_active == 0) { dump_ticks(); return 0; }
         }
     }
@@ -491,6 +503,7 @@ int solve_common(TOSolver* s, int api_mode, const TOALTROOptions& ao, bool sync)
     const TOALOptions& alo = ao.opts_al;
     s->launches = 0;
     s->ticks = 0;
+    for (double& v : s->phase_ms) v = 0.0;
     const bool con = constrained(s);
     const double* X0_in = s->has_X0 ? s->X0 : nullptr;
     CK_RET(s, cudaMemsetAsync(s->queue, 0, 256, s->stream));
@@ -832,6 +845,18 @@ int to_debug_grid(TOHandle s, int which, int32_t* grid, int32_t* smem, uint64_t*
 int to_debug_set_engine(TOHandle s, int32_t engine) {
     if (!s || engine < 0 || engine > 1) return TO_ERR_INVALID;
     s->engine = engine;
+    return 0;
+}
+// per-phase device time of the lockstep engine (diagnostics / roofline): enable, then read after a solve.
+// ms[0..4] = jacobian, backward pass, line-search trials, accept, outer-loop kernels (summed over all ticks)
+int to_debug_phase_timing(TOHandle s, int32_t enable) {
+    if (!s) return TO_ERR_INVALID;
+    s->phase_timing = enable ? 1 : 0;
+    return 0;
+}
+int to_debug_phase_ms(TOHandle s, double* ms) {
+    if (!s || !ms) return TO_ERR_INVALID;
+    for (int i = 0; i < 5; i++) ms[i] = s->phase_ms[i];
     return 0;
 }
 int to_debug_ticks(TOHandle s, int32_t* ticks) {
