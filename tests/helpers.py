@@ -68,3 +68,24 @@ def quadrotor_test_problem(to, kind):
     al = to.AugmentedLagrangianSolverOptions(opts_uncon=il, constraint_tolerance=1e-3, cost_tolerance=1e-5,
                                              cost_tolerance_intermediate=1e-4)
     return p, il, al
+
+
+def pendulum_mintime_test(to):
+    """test/minimum_time_tests.jl:1-63: pendulum rk3, Q=R=Qf=1e-3 I, N=31, bounds +-5 and goal; first a fixed-time ALTRO
+    solve at dt=0.15, then the minimum-time solve (tf=:min, dt=0.075) warm-started with its controls.
+    Returns (make_problem(dt, tf, U0), options)."""
+    import numpy as np
+    n, m, N = 2, 1, 31
+    xf = np.array([np.pi, 0.0])
+
+    def make(dt, tf=float("nan"), U0=None):
+        obj = to.LQRObjective(1e-3 * np.eye(n), 1e-3 * np.eye(m), 1e-3 * np.eye(n), xf, N)
+        cons = to.Constraints(N)
+        bnd = to.BoundConstraint(n, m, u_min=-5.0, u_max=5.0)
+        for k in range(N - 1):
+            cons.add(k, bnd)
+        cons.add(N - 1, to.goal_constraint(xf))
+        return to.Problem(to.rk3(to.Dynamics.pendulum), obj, constraints=cons, x0=np.zeros(n), xf=xf, N=N, dt=dt, tf=tf,
+                          U0=np.ones((N - 1, m)) if U0 is None else U0)
+    al = to.AugmentedLagrangianSolverOptions(iterations=50, penalty_scaling=10.0)
+    return make, to.ALTROSolverOptions(opts_al=al, R_minimum_time=15.0, dt_max=0.15, dt_min=1e-3)

@@ -153,12 +153,17 @@ def test_reference_integration_inequalities(to):
     p.constraints = to.Constraints(p.N)
     to.solve_b(p, to.iLQRSolverOptions())
     assert np.linalg.norm(p.X[-1] - p.xf) < 1e-3
-    p = to.problems.pendulum()
-    tt = p.dt * (p.N - 1)
-    p.tf = 0.0
-    al = to.AugmentedLagrangianSolverOptions(iterations=50, penalty_scaling=10.0)
-    to.solve_b(p, to.ALTROSolverOptions(opts_al=al, R_minimum_time=15.0, dt_max=0.15, dt_min=1e-3))
-    assert to.total_time(p) < 0.5 * tt and to.max_violation(p) < 1e-3
+    # test/minimum_time_tests.jl:36-63: tt_mt < 0.5*tt, tt_mt < 1.0, goal reached, constraints satisfied
+    from helpers import pendulum_mintime_test
+    make, o = pendulum_mintime_test(to)
+    p = make(0.15)
+    to.solve_b(p, o)
+    tt = to.total_time(p)
+    p_mt = make(0.075, tf=0.0, U0=p.U)
+    to.solve_b(p_mt, o)
+    tt_mt = to.total_time(p_mt)
+    assert tt_mt < 0.5 * tt and tt_mt < 1.0
+    assert np.abs(p_mt.X[-1] - p_mt.xf).max() < 1e-3 and to.max_violation(p_mt) < o.opts_al.constraint_tolerance
 
 
 def test_batched_solve_matches_singles_and_is_order_independent(to):

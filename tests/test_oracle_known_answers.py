@@ -210,3 +210,38 @@ def test_oracle_reports_status_instead_of_hanging_or_throwing(oracle):
     prob, opts, x0, X0 = CASES["pend_sqrt_altro"](4)
     r = oracle.solve(prob, opts, x0=x0, X0=X0, B=4, inner_cap=0, outer_cap=0)
     assert np.all(r["results"]["status"] == 0) and np.all(r["results"]["c_max"] < 1e-3)
+
+
+def test_reference_minimum_time_test_inequalities(oracle):
+    """test/minimum_time_tests.jl:36-63 replayed on the oracle: the minimum-time pendulum swing-up takes less than half
+    the fixed-time solution and less than 1 s, reaches the goal and satisfies the constraints.  This is the only
+    reference artefact that pins the minimum-time path."""
+    import trajopt_b200 as to
+    from helpers import pendulum_mintime_test
+    make, o = pendulum_mintime_test(to)
+    p = make(0.15)
+    r = oracle.solve(p, o, x0=p.x0[None], B=1)
+    tt = r["dts"].sum()
+    assert abs(tt - 4.5) < 1e-12 and r["results"]["c_max"][0] < 1e-3
+    p_mt = make(0.075, tf=0.0, U0=r["U"][0])
+    r2 = oracle.solve(p_mt, o, x0=p_mt.x0[None], B=1)
+    tt_mt = r2["dts"].sum()
+    assert tt_mt < 0.5 * tt and tt_mt < 1.0
+    assert np.abs(r2["X"][0, -1] - p_mt.xf).max() < 1e-3 and r2["results"]["c_max"][0] < 1e-3 and r2["results"]["status"][0] == 0
+
+
+def test_reference_quadrotor_test_inequalities(oracle):
+    """test/quadrotor_tests.jl:1-60 replayed on the oracle (rk4 quadrotor, 50 m flight): iLQR reaches xf to 5e-3;
+    AL with the goal constraint and AL with goal + control bounds meet the constraint tolerance."""
+    import trajopt_b200 as to
+    from helpers import quadrotor_test_problem
+    p, il, al = quadrotor_test_problem(to, "none")
+    r = oracle.solve(p, il, x0=p.x0[None], B=1)
+    assert np.linalg.norm(r["X"][0, -1] - p.xf) < 5e-3
+    p, il, al = quadrotor_test_problem(to, "goal")
+    r = oracle.solve(p, al, x0=p.x0[None], B=1)
+    assert np.abs(r["X"][0, -1] - p.xf).max() < 1e-3 and r["results"]["c_max"][0] < 1e-3
+    p, il, al = quadrotor_test_problem(to, "goal+bounds")
+    r = oracle.solve(p, al, x0=p.x0[None], B=1)
+    assert np.linalg.norm(r["X"][0, -1] - p.xf) < 1e-3 and r["results"]["c_max"][0] < 1e-3
+    assert r["U"].min() > -1e-3 and r["U"].max() < 15.0 + 1e-3

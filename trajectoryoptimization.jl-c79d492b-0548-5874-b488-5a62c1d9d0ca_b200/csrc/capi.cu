@@ -48,6 +48,8 @@ struct Variant {
     LsCtl lc{};
     LsGrids grids{};
     int* ls_lists = nullptr;
+    double* cand_alloc = nullptr;  // tail-mode candidate trajectories (lockstep)
+    unsigned int cand_slots = 0;
 };
 
 }  // namespace
@@ -132,6 +134,9 @@ void free_variant(Variant& v) {
     if (v.lc.ws) cudaFree(v.lc.ws);
     if (v.lc.st) cudaFree(v.lc.st);
     if (v.lc.counts) cudaFree(v.lc.counts);
+    if (v.cand_alloc) cudaFree(v.cand_alloc);
+    v.cand_alloc = nullptr;
+    v.cand_slots = 0;
     if (v.ls_lists) cudaFree(v.ls_lists);
     v.lc = LsCtl{};
     v.ls_lists = nullptr;
@@ -303,6 +308,15 @@ int ensure_engine_buffers(TOSolver* s, Variant& v) {
         v.grids.bp = s->sm_count * std::min(s->blocks_per_sm_override, std::max(1, v.grids.occ_bp));
         v.grids.trial = s->sm_count * s->blocks_per_sm_override;
     }
+    // tail mode keeps all 32 candidate trajectories of up to `cand_slots` live problems
+    {
+        unsigned int slots = (unsigned int)s->sm_count * 8u;
+        if (const char* env = getenv("TRAJOPT_B200_TAIL_THRESHOLD")) slots = (unsigned int)atoi(env);  // 0 disables tail mode
+        if (slots > (unsigned int)s->B) slots = (unsigned int)s->B;
+        const size_t per = (size_t)(N * v.ki->n + (N - 1) * v.ki->m) * 32;
+        if (slots > 0 && cudaMalloc(&v.cand_alloc, (size_t)slots * per * sizeof(double)) == cudaSuccess) v.cand_slots = slots;
+        else { cudaGetLastError(); v.cand_alloc = nullptr; v.cand_slots = 0; }
+    }
     v.ls_ready = true;
     return 0;
 }
@@ -325,8 +339,7 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
     const long long max_ticks = (long long)std::max(1, c.o.iterations) * (long long)std::max(1, c.o.opts_uncon.iterations) + 8;
     // tail mode: with few live problems a tick is latency-bound, so every step size is tried in ONE launch
     // (a warp per problem) instead of G at a time
-    unsigned int tail_threshold = (unsigned int)s->sm_count * 8u;
-    if (const char* env = getenv("TRAJOPT_B200_TAIL_THRESHOLD")) tail_threshold = (unsigned int)atoi(env);  // 0 disables tail mode
+    const unsigned int tail_threshold = v.cand_slots;  // 0: tail mode off
     unsigned int known_active = (unsigned int)s->B;  // upper bound (the list only shrinks), refreshed LAG ticks late
     // diagnostics: TRAJOPT_B200_TICK_LOG=<file> records one event per tick and writes "tick ms active" lines
     const char* tick_log = getenv("TRAJOPT_B200_TICK_LOG");
@@ -383,8 +396,11 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
         mark();
         v.ki->ls_launch(c.o.opts_uncon.square_root ? LS_PHASE_BP_SQRT : LS_PHASE_BP, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
         mark();
-        if (known_active <= tail_threshold && ntrial <= 32) {
-            v.ki->ls_launch(LS_PHASE_TRIAL_ALL, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+        const bool tail = (known_active <= tail_threshold && ntrial <= 32);
+        LsCtl lct = v.lc;
+        lct.cand = tail ? v.cand_alloc : nullptr;
+        if (tail) {
+            v.ki->ls_launch(LS_PHASE_TRIAL_ALL, v.grids, st, v.P, Bt, c, lct, cur, 0);
             s->launches -= ngroups - 1;
         } else {
             for (int g = 0; g < ngroups; g++) {
@@ -393,7 +409,7 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
             }
         }
         mark();
-        v.ki->ls_launch(LS_PHASE_ACCEPT, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+        v.ki->ls_launch(tail ? LS_PHASE_ACCEPT_TAIL : LS_PHASE_ACCEPT, v.grids, st, v.P, Bt, c, lct, cur, 0);
         mark();
         v.ki->ls_launch(LS_PHASE_OUTER, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
         CK_RET(s, cudaGetLastError());

@@ -1071,9 +1071,12 @@ template <class C>
 struct Rollout {
     // one closed-loop rollout with step size alpha (rollout.jl:2-23) + its cost (objective.jl:40-48 + AL)
     // WRITE: also store X̄, Ū in place (X <- X̄, U <- Ū) and accumulate the Todorov gradient
-    template <bool WRITE>
+    // CAND: also store the candidate trajectory X̄, Ū in the 32-way interleaved buffers XB / UB (column `slot`), so that the
+    // tail-mode accept kernel copies the winner instead of re-rolling it
+    template <bool WRITE, bool CAND = false>
     static __device__ bool run(const DevProblem& P, const TOiLQROptions& io, double* ws, const WsLayout& L, const double* x0,
-                               double alpha, bool al_on, double& Jt, double& grad_sum) {
+                               double alpha, bool al_on, double& Jt, double& grad_sum, double* XB = nullptr, double* UB = nullptr,
+                               int slot = 0) {
         constexpr int n = C::n, m = C::m;
         const int N = P.N;
         double xb[n], ub[m];
@@ -1118,6 +1121,12 @@ struct Rollout {
 #pragma unroll
                 for (int i = 0; i < m; i++) Uk[i] = ub[i];
             }
+            if (CAND) {
+#pragma unroll
+                for (int i = 0; i < n; i++) XB[((size_t)k * n + i) * 32 + slot] = xb[i];
+#pragma unroll
+                for (int i = 0; i < m; i++) UB[((size_t)k * m + i) * 32 + slot] = ub[i];
+            }
             double xn[n];
             // dyn_eval (augmented model)
             {
@@ -1153,6 +1162,10 @@ struct Rollout {
                 double* XN = ws + L.X + (size_t)(N - 1) * n;
 #pragma unroll
                 for (int i = 0; i < n; i++) XN[i] = xb[i];
+            }
+            if (CAND) {
+#pragma unroll
+                for (int i = 0; i < n; i++) XB[((size_t)(N - 1) * n + i) * 32 + slot] = xb[i];
             }
         }
         Jt = al_on ? (J + Jc) : J;
@@ -1191,7 +1204,16 @@ __global__ void __launch_bounds__(128, MINB) ls_trial_kernel(const DevProblem P,
 #pragma unroll
             for (int i = 0; i < C::n; i++) x0[i] = (i < C::n0) ? Bt.x0[(size_t)b * C::n0 + i] : 0.0;
             double gs;
-            const bool ok = Rollout<C>::template run<false>(P, io, ws, L, x0, alpha, al_on, Jt, gs);
+            bool ok;
+            if (G == 32 && lc.cand != nullptr) {
+                // tail mode: keep every candidate (slot a0 of the candidate buffer, column = trial)
+                const size_t per = (size_t)(P.N * C::n + (P.N - 1) * C::m) * 32;
+                double* XB = lc.cand + (size_t)a0 * per;
+                double* UB = XB + (size_t)P.N * C::n * 32;
+                ok = Rollout<C>::template run<false, true>(P, io, ws, L, x0, alpha, al_on, Jt, gs, XB, UB, trial);
+            } else {
+                ok = Rollout<C>::template run<false>(P, io, ws, L, x0, alpha, al_on, Jt, gs);
+            }
             const double dV0 = st->dV0, dV1 = st->dV1, J_prev = st->J_prev;
             expected = -alpha * (dV0 + alpha * dV1);
             z = (expected > 0) ? (J_prev - Jt) / expected : -1.0;
@@ -1211,6 +1233,89 @@ __global__ void __launch_bounds__(128, MINB) ls_trial_kernel(const DevProblem P,
             } else if (t == 0) {
                 // nobody accepted in this group: next group, or a failed line search
                 if ((grp + 1) * G < ntrial) ls_append(lc.retry[grp & 1], &lc.counts[2 + (grp & 1)], b);
+            }
+        }
+    }
+}
+
+// tail mode: warp per problem; the accepted candidate is copied, not re-rolled (same bookkeeping as ls_accept_kernel,
+// expressed with the warp-level Solver methods)
+template <class C>
+__global__ void __launch_bounds__(32) ls_accept_tail_kernel(const DevProblem P, const DevBatch Bt, const DevCtl ctl, const LsCtl lc, const int cur) {
+    __shared__ Smem<C> sm;
+    const int lane = threadIdx.x;
+    const unsigned int na = lc.counts[cur];
+    const int N = P.N;
+    for (unsigned int a = blockIdx.x; a < na; a += gridDim.x) {
+        const int b = lc.list[cur][a];
+        LsState* st = &lc.st[b];
+        LsSolver<C> s(P, Bt, ctl, sm, lc.ws + (size_t)b * lc.ws_stride, lane);
+        s.load(st, b);
+        const int bp_fail = st->bp_fail, w = st->winner;
+        const double Jwin = st->Jres, ewin = st->exp_res, zwin = st->z_res;
+        __syncwarp();
+        bool inner_done = false;
+        int inner_ok = 1;
+        if (bp_fail) {
+            s.status |= (bp_fail == 2) ? TO_STATUS_NOT_PD_SQRT : TO_STATUS_REG_DIVERGED;
+            if (lane == 0) st->bp_fail = 0;
+            inner_done = true;
+            inner_ok = 0;
+        } else {
+            const int ntrial = s.io.iterations_linesearch + 1;
+            const double J_prev = s.J_prev;
+            double Jres;
+            bool err;
+            if (w >= 0) {
+                s.ls_count += (unsigned long long)(w + 1);
+                Jres = Jwin;
+                s.fp_expected = ewin; s.fp_z = zwin;
+                s.fp_alpha = __longlong_as_double((long long)(1023 - w) << 52);
+                err = (Jres > J_prev);
+                if (!err && !(Jres > s.io.max_cost_value)) {
+                    const size_t per = (size_t)(N * C::n + (N - 1) * C::m) * 32;
+                    const double* XB = lc.cand + (size_t)a * per;
+                    const double* UB = XB + (size_t)N * C::n * 32;
+                    const int nx = N * C::n, nu = (N - 1) * C::m;
+                    for (int e = lane; e < nx; e += 32) s.ws[s.L.X + e] = XB[(size_t)e * 32 + w];
+                    for (int e = lane; e < nu; e += 32) s.ws[s.L.U + e] = UB[(size_t)e * 32 + w];
+                    __syncwarp();
+                }
+            } else {
+                s.ls_count += (unsigned long long)ntrial;
+                Jres = s.eval_cost();
+                s.fp_expected = 0.0; s.fp_z = 0.0; s.fp_alpha = 0.0;
+                s.reg_update(true);
+                s.rho += s.io.bp_reg_fp;
+                err = (Jres > J_prev);
+            }
+            s.steps += 1;
+            if (err) {
+                s.status |= TO_STATUS_COST_INCREASED;
+                inner_done = true;
+                inner_ok = 0;
+            } else if (Jres > s.io.max_cost_value) {
+                s.status |= TO_STATUS_COST_BLOWUP;
+                inner_done = true;
+            } else {
+                const double dJ = fabs(Jres - J_prev);
+                s.J_prev = Jres;
+                s.record_inner(Jres, dJ);
+                if (s.inner_converged()) {
+                    inner_done = true;
+                } else {
+                    s.inner_i += 1;
+                    if (s.inner_i > s.io.iterations) inner_done = true;
+                }
+            }
+        }
+        s.store();
+        if (lane == 0) {
+            if (inner_done) {
+                st->inner_ok = inner_ok;
+                ls_append(lc.outer_list, &lc.counts[4], b);
+            } else {
+                ls_append(lc.list[cur ^ 1], &lc.counts[cur ^ 1], b);
             }
         }
     }
@@ -1454,6 +1559,7 @@ template <class C> void ls_launch_fn(int phase, const LsGrids& g, cudaStream_t s
         case LS_PHASE_TRIAL_ALL: ls_trial_variant<C>(g.trial_minb, true)<<<g.trial, 128, 0, st>>>(P, B, c, lc, cur, 0); break;
         case LS_PHASE_ACCEPT: ls_accept_kernel<C><<<g.accept, 64, 0, st>>>(P, B, c, lc, cur); break;
         case LS_PHASE_OUTER: ls_outer_kernel<C><<<g.outer, 32, 0, st>>>(P, B, c, lc, cur); break;
+        case LS_PHASE_ACCEPT_TAIL: ls_accept_tail_kernel<C><<<g.outer, 32, 0, st>>>(P, B, c, lc, cur); break;
     }
 }
 
