@@ -48,8 +48,9 @@ struct Variant {
     LsCtl lc{};
     LsGrids grids{};
     int* ls_lists = nullptr;
-    double* cand_alloc = nullptr;  // tail-mode candidate trajectories (lockstep)
+    double* cand_alloc = nullptr;  // tail-mode candidate trajectories (lockstep): 32 per list slot
     unsigned int cand_slots = 0;
+    double* cand_bulk = nullptr;   // bulk candidate trajectories: trial_group per problem
 };
 
 }  // namespace
@@ -135,6 +136,8 @@ void free_variant(Variant& v) {
     if (v.lc.st) cudaFree(v.lc.st);
     if (v.lc.counts) cudaFree(v.lc.counts);
     if (v.cand_alloc) cudaFree(v.cand_alloc);
+    if (v.cand_bulk) cudaFree(v.cand_bulk);
+    v.cand_bulk = nullptr;
     v.cand_alloc = nullptr;
     v.cand_slots = 0;
     if (v.ls_lists) cudaFree(v.ls_lists);
@@ -316,6 +319,16 @@ int ensure_engine_buffers(TOSolver* s, Variant& v) {
         const size_t per = (size_t)(N * v.ki->n + (N - 1) * v.ki->m) * 32;
         if (slots > 0 && cudaMalloc(&v.cand_alloc, (size_t)slots * per * sizeof(double)) == cudaSuccess) v.cand_slots = slots;
         else { cudaGetLastError(); v.cand_alloc = nullptr; v.cand_slots = 0; }
+        // bulk: the G candidates of every problem (skipped if it would not leave a quarter of the device memory free)
+        const size_t bulk_bytes = B * (per / 32) * (size_t)v.grids.trial_group * sizeof(double);
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const char* env = getenv("TRAJOPT_B200_BULK_CANDIDATES");
+        const bool want = !(env && env[0] == '0');
+        if (want && bulk_bytes + total_b / 4 < free_b && cudaMalloc(&v.cand_bulk, bulk_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            v.cand_bulk = nullptr;
+        }
     }
     v.ls_ready = true;
     return 0;
@@ -398,18 +411,21 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
         mark();
         const bool tail = (known_active <= tail_threshold && ntrial <= 32);
         LsCtl lct = v.lc;
-        lct.cand = tail ? v.cand_alloc : nullptr;
+        lct.cand = tail ? v.cand_alloc : v.cand_bulk;
+        lct.cand_width = tail ? 32 : v.grids.trial_group;
+        lct.cand_by_problem = tail ? 0 : 1;
+        const bool with_cand = (lct.cand != nullptr);
         if (tail) {
             v.ki->ls_launch(LS_PHASE_TRIAL_ALL, v.grids, st, v.P, Bt, c, lct, cur, 0);
             s->launches -= ngroups - 1;
         } else {
             for (int g = 0; g < ngroups; g++) {
                 if (g >= 2) CK_RET(s, cudaMemsetAsync(v.lc.counts + 2 + (g & 1), 0, sizeof(unsigned int), st));
-                v.ki->ls_launch(LS_PHASE_TRIAL, v.grids, st, v.P, Bt, c, v.lc, cur, g);
+                v.ki->ls_launch(LS_PHASE_TRIAL, v.grids, st, v.P, Bt, c, lct, cur, g);
             }
         }
         mark();
-        v.ki->ls_launch(tail ? LS_PHASE_ACCEPT_TAIL : LS_PHASE_ACCEPT, v.grids, st, v.P, Bt, c, lct, cur, 0);
+        v.ki->ls_launch(with_cand ? LS_PHASE_ACCEPT_TAIL : LS_PHASE_ACCEPT, v.grids, st, v.P, Bt, c, lct, cur, 0);
         mark();
         v.ki->ls_launch(LS_PHASE_OUTER, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
         CK_RET(s, cudaGetLastError());

@@ -89,7 +89,9 @@ struct LsCtl {
     LsState* st;
     double* ws;                    // per-PROBLEM workspaces
     unsigned long long ws_stride;  // doubles per problem
-    double* cand;                  // tail mode: candidate trajectories of the line search, [slot][X|U][element][32 step sizes]; null = off
+    double* cand;                  // candidate trajectories of the line search, [slot][X|U][element][cand_width step sizes]; null = off
+    int cand_width;                // step sizes per launch group (8 in the bulk, 32 in tail mode)
+    int cand_by_problem;           // 1: slot = problem id (bulk buffer), 0: slot = position in the active list (tail buffer)
 };
 
 enum { LS_PHASE_INIT = 0, LS_PHASE_JAC, LS_PHASE_BP, LS_PHASE_TRIAL, LS_PHASE_ACCEPT, LS_PHASE_OUTER, LS_PHASE_TRIAL_ALL, LS_PHASE_BP_SQRT, LS_PHASE_ACCEPT_TAIL };

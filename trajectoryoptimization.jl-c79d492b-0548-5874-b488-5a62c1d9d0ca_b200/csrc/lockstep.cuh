@@ -1073,7 +1073,7 @@ struct Rollout {
     // WRITE: also store X̄, Ū in place (X <- X̄, U <- Ū) and accumulate the Todorov gradient
     // CAND: also store the candidate trajectory X̄, Ū in the 32-way interleaved buffers XB / UB (column `slot`), so that the
     // tail-mode accept kernel copies the winner instead of re-rolling it
-    template <bool WRITE, bool CAND = false>
+    template <bool WRITE, bool CAND = false, int CW = 32>
     static __device__ bool run(const DevProblem& P, const TOiLQROptions& io, double* ws, const WsLayout& L, const double* x0,
                                double alpha, bool al_on, double& Jt, double& grad_sum, double* XB = nullptr, double* UB = nullptr,
                                int slot = 0) {
@@ -1123,9 +1123,9 @@ struct Rollout {
             }
             if (CAND) {
 #pragma unroll
-                for (int i = 0; i < n; i++) XB[((size_t)k * n + i) * 32 + slot] = xb[i];
+                for (int i = 0; i < n; i++) XB[((size_t)k * n + i) * CW + slot] = xb[i];
 #pragma unroll
-                for (int i = 0; i < m; i++) UB[((size_t)k * m + i) * 32 + slot] = ub[i];
+                for (int i = 0; i < m; i++) UB[((size_t)k * m + i) * CW + slot] = ub[i];
             }
             double xn[n];
             // dyn_eval (augmented model)
@@ -1165,7 +1165,7 @@ struct Rollout {
             }
             if (CAND) {
 #pragma unroll
-                for (int i = 0; i < n; i++) XB[((size_t)(N - 1) * n + i) * 32 + slot] = xb[i];
+                for (int i = 0; i < n; i++) XB[((size_t)(N - 1) * n + i) * CW + slot] = xb[i];
             }
         }
         Jt = al_on ? (J + Jc) : J;
@@ -1205,12 +1205,13 @@ __global__ void __launch_bounds__(128, MINB) ls_trial_kernel(const DevProblem P,
             for (int i = 0; i < C::n; i++) x0[i] = (i < C::n0) ? Bt.x0[(size_t)b * C::n0 + i] : 0.0;
             double gs;
             bool ok;
-            if (G == 32 && lc.cand != nullptr) {
-                // tail mode: keep every candidate (slot a0 of the candidate buffer, column = trial)
-                const size_t per = (size_t)(P.N * C::n + (P.N - 1) * C::m) * 32;
-                double* XB = lc.cand + (size_t)a0 * per;
-                double* UB = XB + (size_t)P.N * C::n * 32;
-                ok = Rollout<C>::template run<false, true>(P, io, ws, L, x0, alpha, al_on, Jt, gs, XB, UB, trial);
+            if (lc.cand != nullptr) {
+                // keep every candidate of this group: G-way interleaved, slot = problem id (bulk) or list position (tail),
+                // column = step size within the group; the accept kernel copies the winner instead of re-rolling it
+                const size_t per = (size_t)(P.N * C::n + (P.N - 1) * C::m) * G;
+                double* XB = lc.cand + (size_t)(lc.cand_by_problem ? (unsigned int)b : a0) * per;
+                double* UB = XB + (size_t)P.N * C::n * G;
+                ok = Rollout<C>::template run<false, true, G>(P, io, ws, L, x0, alpha, al_on, Jt, gs, XB, UB, t);
             } else {
                 ok = Rollout<C>::template run<false>(P, io, ws, L, x0, alpha, al_on, Jt, gs);
             }
@@ -1238,8 +1239,8 @@ __global__ void __launch_bounds__(128, MINB) ls_trial_kernel(const DevProblem P,
     }
 }
 
-// tail mode: warp per problem; the accepted candidate is copied, not re-rolled (same bookkeeping as ls_accept_kernel,
-// expressed with the warp-level Solver methods)
+// accept with stored candidates: warp per problem; the accepted candidate is copied, not re-rolled (same bookkeeping as
+// ls_accept_kernel, expressed with the warp-level Solver methods)
 template <class C>
 __global__ void __launch_bounds__(32) ls_accept_tail_kernel(const DevProblem P, const DevBatch Bt, const DevCtl ctl, const LsCtl lc, const int cur) {
     __shared__ Smem<C> sm;
@@ -1273,12 +1274,13 @@ __global__ void __launch_bounds__(32) ls_accept_tail_kernel(const DevProblem P, 
                 s.fp_alpha = __longlong_as_double((long long)(1023 - w) << 52);
                 err = (Jres > J_prev);
                 if (!err && !(Jres > s.io.max_cost_value)) {
-                    const size_t per = (size_t)(N * C::n + (N - 1) * C::m) * 32;
-                    const double* XB = lc.cand + (size_t)a * per;
-                    const double* UB = XB + (size_t)N * C::n * 32;
+                    const int W = lc.cand_width, col = w % W;
+                    const size_t per = (size_t)(N * C::n + (N - 1) * C::m) * W;
+                    const double* XB = lc.cand + (size_t)(lc.cand_by_problem ? (unsigned int)b : a) * per;
+                    const double* UB = XB + (size_t)N * C::n * W;
                     const int nx = N * C::n, nu = (N - 1) * C::m;
-                    for (int e = lane; e < nx; e += 32) s.ws[s.L.X + e] = XB[(size_t)e * 32 + w];
-                    for (int e = lane; e < nu; e += 32) s.ws[s.L.U + e] = UB[(size_t)e * 32 + w];
+                    for (int e = lane; e < nx; e += 32) s.ws[s.L.X + e] = XB[(size_t)e * W + col];
+                    for (int e = lane; e < nu; e += 32) s.ws[s.L.U + e] = UB[(size_t)e * W + col];
                     __syncwarp();
                 }
             } else {
@@ -1529,6 +1531,8 @@ template <class C> int ls_setup_fn(int sm_count, LsGrids* g) {
     g->jac_minb = 2;
     g->trial_minb = 3;
     if constexpr (C::MODEL == 4) {  // quadrotor: kernel variants selectable at run time (tuning)
+        g->jac_pc = 1;    // measured (profiles/r01f): one partial direction per thread at <=168 registers (12 warps/SM)
+        g->jac_minb = 3;  // beats two directions at 255 registers (8 warps/SM): 4.4 vs 5.4 ms per 16,384 problems
         if (const char* env = getenv("TRAJOPT_B200_JAC_PC")) { const int v = atoi(env); if (v == 1 || v == 2) g->jac_pc = v; }
         if (const char* env = getenv("TRAJOPT_B200_JAC_MINB")) { const int v = atoi(env); if (v >= 2 && v <= 4) g->jac_minb = v; }
         if (const char* env = getenv("TRAJOPT_B200_TRIAL_MINB")) { const int v = atoi(env); if (v == 3 || v == 4) g->trial_minb = v; }
