@@ -899,13 +899,18 @@ struct BpGroup {
                 // factorisation and the cost-to-go update run
                 if (k > 0) prefetch(k - 1);
                 tick(4);
+                // Qxx is not needed until the cost-to-go update: park the column in shared memory (T is free now) so the
+                // factorisation below has the registers
+                if (j < n) {
+#pragma unroll
+                    for (int i = 0; i < n; i++) sm.T[j * LDn + i] = Qxxc[i];
+                }
                 // Quu_reg = Quu + rho*I, replicated per lane
-                double Quu[m * m];
                 LU f;
 #pragma unroll
-                for (int e = 0; e < m * m; e++) { Quu[e] = sm.Quu[e]; f.a[e] = Quu[e]; }
+                for (int e = 0; e < m * m; e++) f.a[e] = sm.Quu[e];
 #pragma unroll
-                for (int i = 0; i < m; i++) f.a[i * m + i] = Quu[i * m + i] + rho * 1.0;
+                for (int i = 0; i < m; i++) f.a[i * m + i] = sm.Quu[i * m + i] + rho * 1.0;
                 // the positive-definiteness test and the LU factorisation are independent: no branch between them,
                 // so their dependent chains (sqrt / divide latencies) overlap
                 const bool pd = chol_pd(f.a);
@@ -938,7 +943,7 @@ struct BpGroup {
                     for (int c = 0; c < m; c++) {
                         double acc = 0.0;
 #pragma unroll
-                        for (int l = 0; l < m; l++) acc = fma(Kcol[l], Quu[c * m + l], acc);
+                        for (int l = 0; l < m; l++) acc = fma(Kcol[l], sm.Quu[c * m + l], acc);
                         KQr[c] = acc;
                         sm.KQ[c * LDn + j] = acc;
                     }
@@ -985,7 +990,7 @@ struct BpGroup {
                     }
 #pragma unroll
                     for (int i = 0; i < n; i++) {
-                        Scol[i] = ((Qxxc[i] + b1[i]) + b2[i]) + b3[i];
+                        Scol[i] = ((sm.T[j * LDn + i] + b1[i]) + b2[i]) + b3[i];
                         sm.T[j * LDn + i] = Scol[i];
                     }
                     sm.Sx[j] = Sx_j;
@@ -1007,7 +1012,7 @@ struct BpGroup {
                     for (int c = 0; c < m; c++) {
                         double w = 0.0;
 #pragma unroll
-                        for (int l = 0; l < m; l++) w = fma(0.5 * dk[l], Quu[c * m + l], w);
+                        for (int l = 0; l < m; l++) w = fma(0.5 * dk[l], sm.Quu[c * m + l], w);
                         acc = fma(w, dk[c], acc);
                     }
                     dV1 += acc;
@@ -1067,8 +1072,137 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) ls_bp_kernel(const DevProble
 // ------------------------------------------------------------------------------------------
 // line search: thread per (problem, step size); G consecutive lanes serve one problem
 // ------------------------------------------------------------------------------------------
+// knot_al_cost with the knot's own multiplier / penalty arrays (same arithmetic as knot_al_cost in engine.cuh)
+template <class C>
+TOB_DEV double knot_al_cost_at(const DevProblem& P, int k, const double* lamk, const double* muk, const double* x, const double* u) {
+    const int rb = P.knot_row_begin[k], rc = P.knot_row_count[k];
+    double t1 = 0.0, t2 = 0.0;
+    for (int i = 0; i < rc; i++) {
+        const DevRow r = P.rows[rb + i];
+        const double c = row_value<C>(r, x, u);
+        const double l = lamk[i];
+        const bool act = r.eq ? true : ((c >= 0.0) || (l > 0.0));
+        const double am = act ? muk[i] : 0.0;
+        t1 = fma(l, c, t1);
+        t2 = fma((0.5 * c) * am, c, t2);
+    }
+    return t1 + t2;
+}
+
+template <class C>
+struct RolloutStage {
+    static constexpr int SS = C::n + C::m + C::KDS;  // x_k, u_k, K_k, d_k
+    static constexpr int LC = 16;                    // multipliers / penalties of one knot (larger sets are read from global)
+    static constexpr int SBUF = (SS + 2 * LC + 1) & ~1;
+};
+
 template <class C>
 struct Rollout {
+    // Line-search rollout with the per-knot inputs (x_k, u_k, K_k, d_k, lambda_k, mu_k) staged in shared memory one knot
+    // ahead by cp.async: the `nact` lanes that serve one problem (lane index t within them, warp mask amask) share one
+    // double buffer `stg`.  Arithmetic identical to run<false, CAND, CW>.
+    template <bool CAND, int CW>
+    static __device__ bool run_staged(const DevProblem& P, const TOiLQROptions& io, double* ws, const WsLayout& L, const double* x0,
+                                      double alpha, bool al_on, double& Jt, double* XB, double* UB, int slot, double* stg, int t,
+                                      int nact, unsigned amask) {
+        constexpr int n = C::n, m = C::m;
+        constexpr int SS = RolloutStage<C>::SS, LC = RolloutStage<C>::LC, SBUF = RolloutStage<C>::SBUF;
+        const int N = P.N;
+        const double* lam = ws + L.LAM;
+        const double* mu = ws + L.MU;
+        auto prefetch = [&](int k, int buf) {
+            double* dst = stg + buf * SBUF;
+            const double* xk = ws + L.X + (size_t)k * n;
+            const double* uk = ws + L.U + (size_t)k * m;
+            const double* kd = ws + L.KD + (size_t)k * C::KDS;
+            for (int e = t; e < SS; e += nact) cp_async8(dst + e, (e < n) ? (xk + e) : ((e < n + m) ? (uk + (e - n)) : (kd + (e - n - m))));
+            if (al_on) {
+                const int rc = P.knot_row_count[k], lo = P.knot_lam_off[k];
+                if (rc <= LC)
+                    for (int e = t; e < rc; e += nact) {
+                        cp_async8(dst + SS + e, lam + lo + e);
+                        cp_async8(dst + SS + LC + e, mu + lo + e);
+                    }
+            }
+        };
+        double xb[n], ub[m];
+#pragma unroll
+        for (int i = 0; i < n; i++) xb[i] = x0[i];
+        bool ok = true;
+        double J = 0.0, Jc = 0.0;
+        prefetch(0, 0);
+        for (int k = 0; k < N - 1; k++) {
+            cp_async_wait_all();
+            __syncwarp(amask);  // knot k has landed; every lane is done with the other buffer
+            if (k + 1 < N - 1) prefetch(k + 1, (k + 1) & 1);
+            const double* sk = stg + (k & 1) * SBUF;
+            const double* Xk = sk;
+            const double* Uk = sk + n;
+            const double* Kk = sk + n + m;
+            const double* dk = Kk + m * n;
+            double dx[n];
+#pragma unroll
+            for (int i = 0; i < n; i++) dx[i] = xb[i] - Xk[i];
+#pragma unroll
+            for (int i = 0; i < m; i++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int c = 0; c < n; c++) acc = fma(Kk[c * m + i], dx[c], acc);
+                ub[i] = (Uk[i] + acc) + alpha * dk[i];
+            }
+            J += stage_cost<C>(P, xb, ub);
+            if (al_on) {
+                const int rc = P.knot_row_count[k];
+                const bool staged = (rc <= LC);
+                const int lo = P.knot_lam_off[k];
+                Jc += knot_al_cost_at<C>(P, k, staged ? (sk + SS) : (lam + lo), staged ? (sk + SS + LC) : (mu + lo), xb, ub);
+            }
+            if (CAND) {
+#pragma unroll
+                for (int i = 0; i < n; i++) XB[((size_t)k * n + i) * CW + slot] = xb[i];
+#pragma unroll
+                for (int i = 0; i < m; i++) UB[((size_t)k * m + i) * CW + slot] = ub[i];
+            }
+            double xn[n];
+            {
+                double dt = P.dt;
+                if constexpr (C::MT) {
+                    const double h = ub[m - 1];
+                    dt = h * h;
+                }
+                fd_model<C::MODEL, C::INTEG, double>(xn, xb, ub, dt);
+                if constexpr (C::INF) {
+#pragma unroll
+                    for (int i = 0; i < C::n0; i++) xn[i] = xn[i] + ub[C::m0 + i];
+                }
+                if constexpr (C::MT) xn[n - 1] = ub[m - 1];
+            }
+            double mx = 0.0, mu_ = 0.0;
+            bool bad = false;
+#pragma unroll
+            for (int i = 0; i < n; i++) { const double a = fabs(xn[i]); if (a != a) bad = true; mx = dmax(mx, a); }
+#pragma unroll
+            for (int i = 0; i < m; i++) { const double a = fabs(ub[i]); if (a != a) bad = true; mu_ = dmax(mu_, a); }
+            if (bad || !(mx < io.max_state_value && mu_ < io.max_control_value)) ok = false;
+#pragma unroll
+            for (int i = 0; i < n; i++) xb[i] = xn[i];
+        }
+        {
+            double uz[m];
+#pragma unroll
+            for (int i = 0; i < m; i++) uz[i] = 0.0;
+            J += term_cost<C>(P, xb);
+            if (al_on) Jc += knot_al_cost<C>(P, N - 1, lam, mu, xb, uz);
+            if (CAND) {
+#pragma unroll
+                for (int i = 0; i < n; i++) XB[((size_t)(N - 1) * n + i) * CW + slot] = xb[i];
+            }
+        }
+        __syncwarp(amask);  // nobody reads the staging buffers any more
+        Jt = al_on ? (J + Jc) : J;
+        return ok;
+    }
+
     // one closed-loop rollout with step size alpha (rollout.jl:2-23) + its cost (objective.jl:40-48 + AL)
     // WRITE: also store X̄, Ū in place (X <- X̄, U <- Ū) and accumulate the Todorov gradient
     // CAND: also store the candidate trajectory X̄, Ū in the 32-way interleaved buffers XB / UB (column `slot`), so that the
@@ -1181,6 +1315,7 @@ __global__ void __launch_bounds__(128, MINB) ls_trial_kernel(const DevProblem P,
     const int* list = (grp == 0) ? lc.list[cur] : lc.retry[(grp - 1) & 1];
     const unsigned int na = (grp == 0) ? lc.counts[cur] : lc.counts[2 + ((grp - 1) & 1)];
     // (the host zeroes counts[2 + (grp & 1)] before launching a group >= 2)
+    __shared__ __align__(16) double stage_all[(128 / G) * 2 * RolloutStage<C>::SBUF];
     const WsLayout L = ws_layout<C>(P.N, P.Ptot, false);
     const bool al_on = (ctl.mode == 1);
     const int lane = threadIdx.x & 31;
@@ -1198,12 +1333,16 @@ __global__ void __launch_bounds__(128, MINB) ls_trial_kernel(const DevProblem P,
         double Jt = 0.0, expected = 0.0, z = 0.0;
         const double alpha = __longlong_as_double((long long)(1023 - trial) << 52);  // 2^-trial
         const bool bp_fail = valid && (st->bp_fail != 0);  // backward pass aborted: no line search for this problem
-        if (valid && !bp_fail && trial < ntrial) {
+        const bool runs = valid && !bp_fail && trial < ntrial;
+        const unsigned amask = __ballot_sync(0xffffffffu, runs);
+        if (runs) {
             double* ws = lc.ws + (size_t)b * lc.ws_stride;
             double x0[C::n];
 #pragma unroll
             for (int i = 0; i < C::n; i++) x0[i] = (i < C::n0) ? Bt.x0[(size_t)b * C::n0 + i] : 0.0;
-            double gs;
+            const unsigned gm_ = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - t));
+            const int nact = __popc(amask & gm_);  // lanes serving this problem (the first nact of its group)
+            double* stg = stage_all + (size_t)(threadIdx.x / G) * 2 * RolloutStage<C>::SBUF;
             bool ok;
             if (lc.cand != nullptr) {
                 // keep every candidate of this group: G-way interleaved, slot = problem id (bulk) or list position (tail),
@@ -1211,9 +1350,9 @@ __global__ void __launch_bounds__(128, MINB) ls_trial_kernel(const DevProblem P,
                 const size_t per = (size_t)(P.N * C::n + (P.N - 1) * C::m) * G;
                 double* XB = lc.cand + (size_t)(lc.cand_by_problem ? (unsigned int)b : a0) * per;
                 double* UB = XB + (size_t)P.N * C::n * G;
-                ok = Rollout<C>::template run<false, true, G>(P, io, ws, L, x0, alpha, al_on, Jt, gs, XB, UB, t);
+                ok = Rollout<C>::template run_staged<true, G>(P, io, ws, L, x0, alpha, al_on, Jt, XB, UB, t, stg, t, nact, amask);
             } else {
-                ok = Rollout<C>::template run<false>(P, io, ws, L, x0, alpha, al_on, Jt, gs);
+                ok = Rollout<C>::template run_staged<false, G>(P, io, ws, L, x0, alpha, al_on, Jt, nullptr, nullptr, 0, stg, t, nact, amask);
             }
             const double dV0 = st->dV0, dV1 = st->dV1, J_prev = st->J_prev;
             expected = -alpha * (dV0 + alpha * dV1);
