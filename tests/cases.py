@@ -31,6 +31,19 @@ def _pend_altro(B):
     return p, api.ALTROSolverOptions(), problems.batch_x0("pendulum", B) * 0.2, None
 
 
+def _pend_integrator(integ):
+    """test/pendulum_tests.jl:9-27: the pendulum ALTRO solve over the explicit integration schemes"""
+    def make(B):
+        p = problems.pendulum()
+        p.model = {"rk4": api.rk4, "midpoint": api.midpoint}[integ](api.Dynamics.pendulum)
+        al = api.AugmentedLagrangianSolverOptions(iterations=50, penalty_scaling=10.0)
+        o = api.ALTROSolverOptions(opts_al=al, R_minimum_time=15.0, dt_max=0.15, dt_min=1e-3)
+        x0 = problems.batch_x0("pendulum", B) * 0.2
+        x0[0] = 0.0
+        return p, o, x0, None
+    return make
+
+
 def _quad(B):
     p = problems.quadrotor()
     return p, problems.quadrotor_bench_options(), problems.batch_x0("quadrotor", B), None
@@ -169,6 +182,8 @@ CASES = {
     "park_altro": _park,
     "park_inf_altro": _park_inf,
     "pend_mintime": _pend_mintime,
+    "pend_rk4_altro": _pend_integrator("rk4"),
+    "pend_midpoint_altro": _pend_integrator("midpoint"),
     "pend_sqrt_altro": _pend_sqrt_altro,
     "dp_sqrt_ilqr": _dp_sqrt_ilqr,
     "acrobot_sqrt_al": _acrobot_sqrt_al,

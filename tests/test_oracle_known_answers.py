@@ -245,3 +245,13 @@ def test_reference_quadrotor_test_inequalities(oracle):
     r = oracle.solve(p, al, x0=p.x0[None], B=1)
     assert np.linalg.norm(r["X"][0, -1] - p.xf) < 1e-3 and r["results"]["c_max"][0] < 1e-3
     assert r["U"].min() > -1e-3 and r["U"].max() < 15.0 + 1e-3
+
+
+def test_reference_pendulum_integrator_sweep(oracle):
+    """test/pendulum_tests.jl:9-27 (explicit schemes): ALTRO on the pendulum with midpoint / rk3 / rk4 meets the
+    constraint tolerance."""
+    from cases import CASES
+    for name in ("pend_altro", "pend_rk4_altro", "pend_midpoint_altro"):
+        prob, opts, x0, X0 = CASES[name](1)
+        r = oracle.solve(prob, opts, x0=prob.x0[None], B=1)
+        assert r["results"]["c_max"][0] < 1e-3 and r["results"]["status"][0] == 0, name

@@ -20,13 +20,22 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC",
 
 # (model, integrator, infeasible, min_time, partials per lane)
 INSTANCES = [
+    # rk3: every model, plus the ALTRO transforms the problem zoo uses (infeasible start, minimum time)
     (0, 0, 0, 0, 3),
     (1, 0, 0, 0, 3), (1, 0, 0, 1, 4),
-    (2, 0, 0, 0, 5), (2, 0, 1, 0, 5), (2, 0, 0, 1, 6), (2, 1, 0, 0, 5),
+    (2, 0, 0, 0, 5), (2, 0, 1, 0, 5), (2, 0, 0, 1, 6),
     (3, 0, 0, 0, 5),
-    (4, 0, 0, 0, 2), (4, 1, 0, 0, 2),
+    (4, 0, 0, 0, 2),
     (5, 0, 0, 0, 5), (5, 0, 0, 1, 6),
     (6, 0, 0, 0, 6), (6, 0, 0, 1, 7),
+    # rk4 and midpoint (src/integration.jl:115-125, 26-33): every model
+    (0, 1, 0, 0, 3), (0, 2, 0, 0, 3),
+    (1, 1, 0, 0, 3), (1, 2, 0, 0, 3),
+    (2, 1, 0, 0, 5), (2, 2, 0, 0, 5),
+    (3, 1, 0, 0, 5), (3, 2, 0, 0, 5),
+    (4, 1, 0, 0, 2), (4, 2, 0, 0, 2),
+    (5, 1, 0, 0, 5), (5, 2, 0, 0, 5),
+    (6, 1, 0, 0, 6), (6, 2, 0, 0, 6),
 ]
 
 

@@ -104,14 +104,16 @@ int fail_create(int code, const std::string& msg) {
     return code;
 }
 
+// "diagonal" / "zero" in the bit-exact sense the kernels rely on: the other entries are +0.0 (a -0.0 would give -0.0*dt)
+bool is_pzero(double v) { return v == 0.0 && !std::signbit(v); }
 bool is_diag(const std::vector<double>& M, int n) {
     for (int j = 0; j < n; j++)
         for (int i = 0; i < n; i++)
-            if (i != j && M[(size_t)j * n + i] != 0.0) return false;
+            if (i != j && !is_pzero(M[(size_t)j * n + i])) return false;
     return true;
 }
 bool is_zero(const std::vector<double>& M) {
-    for (double v : M) if (v != 0.0) return false;
+    for (double v : M) if (!is_pzero(v)) return false;
     return true;
 }
 
@@ -259,6 +261,7 @@ int build_variant(TOSolver* s, int which, const TOALTROOptions* ao) {
     }
     lo[N] = off;
     P.Ptot = off;
+    P.nrows = (int)rows.size();
     if ((rc = upload(s, v, rows, &P.rows))) return rc;
     if ((rc = upload(s, v, kb, &P.knot_row_begin))) return rc;
     if ((rc = upload(s, v, kc, &P.knot_row_count))) return rc;
@@ -301,7 +304,7 @@ int ensure_engine_buffers(TOSolver* s, Variant& v) {
     v.lc.list[0] = v.ls_lists; v.lc.list[1] = v.ls_lists + B;
     v.lc.retry[0] = v.ls_lists + 2 * B; v.lc.retry[1] = v.ls_lists + 3 * B;
     v.lc.outer_list = v.ls_lists + 4 * B;
-    int rc = v.ki->ls_setup(s->sm_count, &v.grids);
+    int rc = v.ki->ls_setup(s->sm_count, N, v.P.nrows, &v.grids);
     if (rc != 0) {
         snprintf(buf, sizeof buf, "lockstep kernel setup failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
         return s->fail(TO_ERR_CUDA, buf);

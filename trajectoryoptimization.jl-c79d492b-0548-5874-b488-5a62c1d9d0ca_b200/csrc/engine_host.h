@@ -19,6 +19,7 @@ struct DevRow {
 
 struct DevProblem {
     int N, Ptot;
+    int nrows, pad0;  // entries of rows[]
     double dt, R_mt;
     const double *Q, *R, *H, *q, *r, *Qf, *qf;  // dims nq / mq of the wrapped QuadraticCost
     double c, cf;
@@ -100,7 +101,8 @@ struct LsGrids {
     int bp_smem, bp_groups_per_block, trial_group;
     int occ_jac, occ_bp, occ_trial;
     int jac_pc;  // partial directions per thread in the Jacobian kernel
-    int jac_minb, trial_minb, bp_minb;  // __launch_bounds__ min-blocks variants (register caps)
+    int jac_minb, trial_minb, bp_minb;
+    int tab_bytes;  // dynamic shared memory of the per-block copy of the knot tables / constraint rows  // __launch_bounds__ min-blocks variants (register caps)
 };
 
 // host-visible launcher table entry
@@ -114,7 +116,7 @@ struct KernelInfo {
     void (*launch)(int grid, cudaStream_t st, const DevProblem& P, const DevBatch& B, const DevCtl& c);
     // lockstep engine
     unsigned long long (*ls_ws_doubles)(int N, int Ptot);
-    int (*ls_setup)(int sm_count, LsGrids* g);
+    int (*ls_setup)(int sm_count, int N, int nrows, LsGrids* g);
     void (*ls_launch)(int phase, const LsGrids& g, cudaStream_t st, const DevProblem& P, const DevBatch& B, const DevCtl& c,
                       const LsCtl& lc, int cur, int grp);
 };

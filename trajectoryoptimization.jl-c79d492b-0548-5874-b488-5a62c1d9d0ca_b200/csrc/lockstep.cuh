@@ -199,6 +199,34 @@ struct LsSolver : Solver<C> {
     }
 };
 
+// Per-block shared-memory copy of the problem's knot tables (first row / row count / multiplier offset per knot) and,
+// when they are few, of the constraint rows: every knot of every live problem looks these up, and a chain of dependent
+// global loads per knot is what a latency-bound kernel can least afford.  The copy is reached through the same
+// DevProblem fields (generic pointers into shared memory).
+constexpr int LS_ROWCAP = 64;
+__host__ __device__ inline int ls_tab_bytes(int N, int nrows) {
+    const int tab = ((3 * N + 1) * 4 + 15) & ~15;
+    return tab + ((nrows <= LS_ROWCAP) ? nrows * (int)sizeof(DevRow) : 0);
+}
+__device__ inline void ls_stage_problem(DevProblem& Pl, const DevProblem& P, unsigned char* smem_tab) {
+    const int N = P.N;
+    int* tab = reinterpret_cast<int*>(smem_tab);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        tab[i] = P.knot_row_begin[i];
+        tab[N + i] = P.knot_row_count[i];
+    }
+    for (int i = threadIdx.x; i <= N; i += blockDim.x) tab[2 * N + i] = P.knot_lam_off[i];
+    Pl.knot_row_begin = tab;
+    Pl.knot_row_count = tab + N;
+    Pl.knot_lam_off = tab + 2 * N;
+    if (P.nrows <= LS_ROWCAP) {
+        DevRow* rows = reinterpret_cast<DevRow*>(smem_tab + (((3 * N + 1) * 4 + 15) & ~15));
+        for (int i = threadIdx.x; i < P.nrows; i += blockDim.x) rows[i] = P.rows[i];
+        Pl.rows = rows;
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void ls_append(int* list, unsigned int* count, int b) {
     const unsigned int pos = atomicAdd(count, 1u);
     list[pos] = b;
@@ -367,6 +395,16 @@ struct BpGroup {
     // register-resident columns
     double Scol[n], Qxxc[n], Quxc[m], Quuc[m], Kcol[m];
     double Qx_j, Qu_j, Sx_j;
+    // diagonal stage cost (every LQRObjective of the problem zoo): the lane's own diagonal / linear entries, loaded once
+    bool fast_cost = false;
+    double qjj = 0.0, qlin = 0.0, rjj = 0.0, rlin = 0.0;
+    __device__ void load_cost_constants() {
+        fast_cost = !C::MT && P.q_diag && P.r_diag && P.h_zero;
+        if (fast_cost) {
+            if (j < nq) { qjj = __ldg(&P.Q[j * nq + j]); qlin = __ldg(&P.q[j]); }
+            if (j < mq) { rjj = __ldg(&P.R[j * mq + j]); rlin = __ldg(&P.r[j]); }
+        }
+    }
     // optional cycle profile of one group (diagnostics: to_debug_enable): cycles per section of the knot loop
     long long* prof = nullptr;
     long long pt0 = 0;
@@ -521,6 +559,41 @@ struct BpGroup {
                     }
                 }
             }
+        }
+        if (fast_cost && !term) {
+            // diagonal Q, R and H = 0 (flags checked on the host: off-diagonal entries are exactly +0.0): column j of the
+            // stage blocks is Q_jj*dt at the diagonal and +0.0 elsewhere -- the same values the general path computes
+            const double dt = P.dt;
+            if (j < n) {
+                const double vqx = (j < nq) ? ((fma(qjj, xs[j], 0.0) + qlin) + 0.0) : 0.0;
+                const double qd_ = qjj * dt;
+#pragma unroll
+                for (int i = 0; i < n; i++) {
+                    const double v = (i == j && j < nq) ? qd_ : ((i < nq && j < nq) ? 0.0 * dt : 0.0);
+                    const double acc = (i == j) ? dxx : Qxxc[i];
+                    Qxxc[i] = has_al ? (v + acc) : v;
+                }
+                const double v = (j < nq) ? vqx * dt : 0.0;
+                Qx_j = has_al ? (v + ax) : v;
+#pragma unroll
+                for (int i = 0; i < m; i++) {
+                    const double w = (i < mq && j < nq) ? (0.0 * dt) : 0.0;
+                    Quxc[i] = has_al ? (w + Quxc[i]) : w;
+                }
+            }
+            if (j < m) {
+                const double vqu = (j < mq) ? ((fma(rjj, xs[n + j], 0.0) + rlin) + 0.0) : 0.0;
+                const double rd_ = rjj * dt;
+#pragma unroll
+                for (int i = 0; i < m; i++) {
+                    const double v = (i == j && j < mq) ? rd_ : ((i < mq && j < mq) ? 0.0 * dt : 0.0);
+                    const double acc = (i == j) ? duu : Quuc[i];
+                    Quuc[i] = has_al ? (v + acc) : v;
+                }
+                const double v = (j < mq) ? vqu * dt : 0.0;
+                Qu_j = has_al ? (v + au) : v;
+            }
+            return;
         }
         // the wrapped quadratic cost: own entries of the unscaled gradients
         const double* Qm = term ? P.Qf : P.Q;
@@ -1038,10 +1111,12 @@ struct BpGroup {
 };
 
 template <class C, int WARPS, int MINB>
-__global__ void __launch_bounds__(32 * WARPS, MINB) ls_bp_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
+__global__ void __launch_bounds__(32 * WARPS, MINB) ls_bp_kernel(const DevProblem Pg, const DevCtl ctl, const LsCtl lc, const int cur) {
     constexpr int GS = ls_group_size<C>();
     constexpr int GPB = (32 / GS) * WARPS;  // groups per block
     extern __shared__ __align__(16) unsigned char ls_smem_raw[];
+    DevProblem P = Pg;
+    ls_stage_problem(P, Pg, ls_smem_raw + (size_t)GPB * ls_bp_stride<C>());
     BpSmem<C>& smem_g = *reinterpret_cast<BpSmem<C>*>(ls_smem_raw + (size_t)(threadIdx.x / GS) * ls_bp_stride<C>());
     const unsigned int na = lc.counts[cur];
     const int g = threadIdx.x / GS, j = threadIdx.x % GS;
@@ -1057,6 +1132,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) ls_bp_kernel(const DevProble
             BpGroup<C> G(P, smem_g, lc.ws + (size_t)b * lc.ws_stride, j, gmask, al_on, io);
             G.rho = st->rho;
             G.drho = st->drho;
+            G.load_cost_constants();
             if (ctl.debug && a == 0) G.prof = reinterpret_cast<long long*>(ctl.debug);
             double dV0, dV1;
             const bool ok = G.run(dV0, dV1);
@@ -1310,8 +1386,11 @@ struct Rollout {
 
 // group `grp` of G step sizes: trials grp*G .. grp*G+G-1 (alpha = 2^-trial)
 template <class C, int G, int MINB>
-__global__ void __launch_bounds__(128, MINB) ls_trial_kernel(const DevProblem P, const DevBatch Bt, const DevCtl ctl, const LsCtl lc,
+__global__ void __launch_bounds__(128, MINB) ls_trial_kernel(const DevProblem Pg, const DevBatch Bt, const DevCtl ctl, const LsCtl lc,
                                                        const int cur, const int grp) {
+    extern __shared__ __align__(16) unsigned char ls_tab_raw[];
+    DevProblem P = Pg;
+    ls_stage_problem(P, Pg, ls_tab_raw);
     const int* list = (grp == 0) ? lc.list[cur] : lc.retry[(grp - 1) & 1];
     const unsigned int na = (grp == 0) ? lc.counts[cur] : lc.counts[2 + ((grp - 1) & 1)];
     // (the host zeroes counts[2 + (grp & 1)] before launching a group >= 2)
@@ -1650,9 +1729,10 @@ template <class C> LsTrialFn ls_trial_variant(int minb, bool all) {
 
 template <class C> unsigned long long ls_ws_doubles_fn(int N, int Ptot) { return ws_layout<C>(N, Ptot, false).total; }
 
-template <class C> int ls_setup_fn(int sm_count, LsGrids* g) {
+template <class C> int ls_setup_fn(int sm_count, int N, int nrows, LsGrids* g) {
     constexpr int GPB = (32 / ls_group_size<C>()) * LS_BP_WARPS;
-    g->bp_smem = ls_bp_stride<C>() * GPB;
+    g->tab_bytes = ls_tab_bytes(N, nrows);
+    g->bp_smem = ls_bp_stride<C>() * GPB + g->tab_bytes;
     g->bp_groups_per_block = GPB;
     g->trial_group = LS_TRIAL_G;
     g->bp_minb = 3;
@@ -1683,7 +1763,7 @@ template <class C> int ls_setup_fn(int sm_count, LsGrids* g) {
     if (nb < 1) return -2;
     g->bp = sm_count * nb;
     g->occ_bp = nb;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_trial_variant<C>(g->trial_minb, false), 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_trial_variant<C>(g->trial_minb, false), 128, g->tab_bytes);
     g->trial = sm_count * (nb > 0 ? nb : 1);
     g->occ_trial = nb;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_accept_kernel<C>, 64, 0);
@@ -1698,8 +1778,8 @@ template <class C> void ls_launch_fn(int phase, const LsGrids& g, cudaStream_t s
         case LS_PHASE_JAC: ls_jac_variant<C>(g.jac_pc, g.jac_minb)<<<g.jac, 128, 0, st>>>(P, lc, cur); break;
         case LS_PHASE_BP: ls_bp_variant<C>(g.bp_minb)<<<g.bp, 32 * LS_BP_WARPS, g.bp_smem, st>>>(P, c, lc, cur); break;
         case LS_PHASE_BP_SQRT: ls_bp_sqrt_kernel<C><<<g.accept, 64, 0, st>>>(P, c, lc, cur); break;
-        case LS_PHASE_TRIAL: ls_trial_variant<C>(g.trial_minb, false)<<<g.trial, 128, 0, st>>>(P, B, c, lc, cur, grp); break;
-        case LS_PHASE_TRIAL_ALL: ls_trial_variant<C>(g.trial_minb, true)<<<g.trial, 128, 0, st>>>(P, B, c, lc, cur, 0); break;
+        case LS_PHASE_TRIAL: ls_trial_variant<C>(g.trial_minb, false)<<<g.trial, 128, g.tab_bytes, st>>>(P, B, c, lc, cur, grp); break;
+        case LS_PHASE_TRIAL_ALL: ls_trial_variant<C>(g.trial_minb, true)<<<g.trial, 128, g.tab_bytes, st>>>(P, B, c, lc, cur, 0); break;
         case LS_PHASE_ACCEPT: ls_accept_kernel<C><<<g.accept, 64, 0, st>>>(P, B, c, lc, cur); break;
         case LS_PHASE_OUTER: ls_outer_kernel<C><<<g.outer, 32, 0, st>>>(P, B, c, lc, cur); break;
         case LS_PHASE_ACCEPT_TAIL: ls_accept_tail_kernel<C><<<g.outer, 32, 0, st>>>(P, B, c, lc, cur); break;
