@@ -263,9 +263,17 @@ __global__ void __launch_bounds__(32) ls_outer_kernel(const DevProblem P, const 
 }
 
 // ---- Jacobians: thread per (problem, knot, chunk of partial directions) -----------------------
+// Leading state directions the continuous dynamics do not depend on (quadrotor: the position r, dynamics/quadrotor.jl:
+// only q, v, omega enter f).  For those the dual-number rk3 yields the unit column exactly (every partial is 0*finite,
+// and x.p + (+-0) = x.p), so the Jacobian kernel writes e_c instead of pushing a dual through the integrator -- unless
+// an input is not finite, in which case the directions are computed the long way to keep NaN patterns identical.
+template <int MODEL> struct TrivialDirs { static constexpr int value = 0; };
+template <> struct TrivialDirs<4> { static constexpr int value = 3; };
+
 template <class C, int PC, int MINB>
 __global__ void __launch_bounds__(128, MINB) ls_jac_kernel(const DevProblem P, const LsCtl lc, const int cur) {
-    constexpr int NCH = (C::PT + PC - 1) / PC;
+    constexpr int TZ = (PC == 1 && !C::MT) ? TrivialDirs<C::MODEL>::value : 0;
+    constexpr int NCH = (C::PT - TZ + PC - 1) / PC;
     typedef Dual<PC> D;
     const unsigned int na = lc.counts[cur];
     if (blockIdx.x == 0 && threadIdx.x == 0) { lc.counts[cur ^ 1] = 0; lc.counts[2] = 0; lc.counts[3] = 0; lc.counts[4] = 0; }
@@ -278,10 +286,28 @@ __global__ void __launch_bounds__(128, MINB) ls_jac_kernel(const DevProblem P, c
         const int b = lc.list[cur][a];
         double* ws = lc.ws + (size_t)b * lc.ws_stride;
         const int k = it / NCH, ch = it - k * NCH;
-        const int s0 = ch * PC;
-        D xs[C::n0], us[C::m0], dts, xn[C::n0];
         const double* xk = ws + L.X + (size_t)k * C::n;
         const double* uk = ws + L.U + (size_t)k * C::m;
+        double* ab = ws + L.Z + (size_t)k * C::ZA;
+        int nrep = 1;
+        if (TZ > 0 && ch == 0) {
+            bool fin = true;
+#pragma unroll
+            for (int i = 0; i < C::n0; i++) fin = fin && isfinite(xk[i]);
+#pragma unroll
+            for (int i = 0; i < C::m0; i++) fin = fin && isfinite(uk[i]);
+            if (fin) {
+#pragma unroll
+                for (int c = 0; c < TZ; c++)
+#pragma unroll
+                    for (int i = 0; i < C::n0; i++) ab[i * C::LDZ + c] = (i == c) ? 1.0 : 0.0;
+            } else {
+                nrep = 1 + TZ;
+            }
+        }
+      for (int rep = 0; rep < nrep; rep++) {
+        const int s0 = (rep == 0) ? (TZ + ch * PC) : (rep - 1);
+        D xs[C::n0], us[C::m0], dts, xn[C::n0];
 #pragma unroll
         for (int i = 0; i < C::n0; i++) {
             xs[i] = D(xk[i]);
@@ -307,7 +333,6 @@ __global__ void __launch_bounds__(128, MINB) ls_jac_kernel(const DevProblem P, c
         fd_model<C::MODEL, C::INTEG, D>(xn, xs, us, dts);
         // row-major [A_k B_k] of the AUGMENTED model, rows of C::LDZ doubles
         // (add_slack_controls: src/model.jl:761-779; add_min_time_controls: minimum_time.jl:85-104)
-        double* ab = ws + L.Z + (size_t)k * C::ZA;
         double h2 = 0.0;
         if constexpr (C::MT) h2 = 2.0 * uk[C::m - 1];
 #pragma unroll
@@ -320,6 +345,7 @@ __global__ void __launch_bounds__(128, MINB) ls_jac_kernel(const DevProblem P, c
                 for (int i = 0; i < C::n0; i++) ab[i * C::LDZ + col] = is_dt ? xn[i].p[j] * h2 : xn[i].p[j];
             }
         }
+      }
         if (ch == 0 && (C::INF || C::MT)) {
             // the constant entries of the augmented Jacobian
             for (int i = 0; i < C::n; i++)
