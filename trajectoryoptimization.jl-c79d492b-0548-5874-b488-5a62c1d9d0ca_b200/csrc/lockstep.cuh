@@ -272,7 +272,7 @@ template <> struct TrivialDirs<4> { static constexpr int value = 3; };
 
 template <class C, int PC, int MINB>
 __global__ void __launch_bounds__(128, MINB) ls_jac_kernel(const DevProblem P, const LsCtl lc, const int cur) {
-    constexpr int TZ = (PC == 1 && !C::MT) ? TrivialDirs<C::MODEL>::value : 0;
+    constexpr int TZ = (!C::MT) ? TrivialDirs<C::MODEL>::value : 0;
     constexpr int NCH = (C::PT - TZ + PC - 1) / PC;
     typedef Dual<PC> D;
     const unsigned int na = lc.counts[cur];
@@ -302,11 +302,11 @@ __global__ void __launch_bounds__(128, MINB) ls_jac_kernel(const DevProblem P, c
 #pragma unroll
                     for (int i = 0; i < C::n0; i++) ab[i * C::LDZ + c] = (i == c) ? 1.0 : 0.0;
             } else {
-                nrep = 1 + TZ;
+                nrep = 1 + (TZ + PC - 1) / PC;
             }
         }
       for (int rep = 0; rep < nrep; rep++) {
-        const int s0 = (rep == 0) ? (TZ + ch * PC) : (rep - 1);
+        const int s0 = (rep == 0) ? (TZ + ch * PC) : (rep - 1) * PC;  // long way: directions 0..TZ-1, PC at a time (c < TZ guard below)
         D xs[C::n0], us[C::m0], dts, xn[C::n0];
 #pragma unroll
         for (int i = 0; i < C::n0; i++) {
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(128, MINB) ls_jac_kernel(const DevProblem P, c
 #pragma unroll
         for (int j = 0; j < PC; j++) {
             const int c = s0 + j;
-            if (c < C::PT) {
+            if (c < C::PT && (rep == 0 || c < TZ)) {
                 const int col = (c < C::n0) ? c : ((c < C::n0 + C::m0) ? C::n + (c - C::n0) : C::n + C::m - 1);
                 const bool is_dt = (C::MT && c == C::n0 + C::m0);
 #pragma unroll

@@ -159,6 +159,7 @@ TOB_DEV double div6(double x) {
         const double r = fma(-6.0, q, x);
         return fma(r, y, q);
     }
+    if (x == 0.0) return x;  // +-0 / 6 = +-0: most dual partials are exact zeros, keep them off the division subroutine
     return x / 6.0;
 }
 TOB_DEV double div6_t(double x) { return div6(x); }
