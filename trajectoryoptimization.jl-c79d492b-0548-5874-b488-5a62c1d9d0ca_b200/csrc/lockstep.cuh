@@ -905,20 +905,11 @@ struct BpGroup {
                 gsync();  // knot k's inputs have landed; every lane is done with knot k+1
                 const double* AB = sm.AB;
                 tick(0);
-                if (store_mode && k >= stored_from) {
-                    q_load(k);
-                } else {
-                    const int rc = P.knot_row_count[k], lo = P.knot_lam_off[k];
-                    const bool staged = (rc <= LAMCAP);
-                    expansion(k, sm.xu, staged ? sm.lam : ws + L.LAM + lo, staged ? sm.mu : ws + L.MU + lo);
-                }
-                tick(1);
-                // Qx += A'Sx ; Qu += B'Sx ; T = A'S (column j) ; Tu = B'S (column j)
+                // T = A'S (column j) ; Tu = B'S (column j) ; the A'Sx, B'Sx sums
+                double accA = 0.0, accB = 0.0;
                 if (j < n) {
-                    double acc = 0.0;
 #pragma unroll
-                    for (int l = 0; l < n; l++) acc = fma(AB[l * LDZ + j], sm.Sx[l], acc);
-                    Qx_j += acc;
+                    for (int l = 0; l < n; l++) accA = fma(AB[l * LDZ + j], sm.Sx[l], accA);
                     double t[n], tu[m];
 #pragma unroll
                     for (int i = 0; i < n; i++) t[i] = 0.0;
@@ -938,20 +929,18 @@ struct BpGroup {
                     for (int i = 0; i < m; i++) sm.Tu[j * LDm + i] = tu[i];
                 }
                 if (j < m) {
-                    double acc = 0.0;
 #pragma unroll
-                    for (int l = 0; l < n; l++) acc = fma(AB[l * LDZ + n + j], sm.Sx[l], acc);
-                    Qu_j += acc;
+                    for (int l = 0; l < n; l++) accB = fma(AB[l * LDZ + n + j], sm.Sx[l], accB);
                 }
                 gsync();
-                tick(2);
-                // Qxx += T*A ; Qux += Tu*A ; Quu += Tu*B
+                tick(1);
+                // T*A, Tu*A, Tu*B (column j), accumulated from zero
+                double a1[n], a2[m], a3[m];
+#pragma unroll
+                for (int i = 0; i < n; i++) a1[i] = 0.0;
+#pragma unroll
+                for (int i = 0; i < m; i++) { a2[i] = 0.0; a3[i] = 0.0; }
                 if (j < n) {
-                    double a1[n], a2[m];
-#pragma unroll
-                    for (int i = 0; i < n; i++) a1[i] = 0.0;
-#pragma unroll
-                    for (int i = 0; i < m; i++) a2[i] = 0.0;
 #pragma unroll
                     for (int l = 0; l < n; l++) {
                         const double a_l = AB[l * LDZ + j];
@@ -960,21 +949,34 @@ struct BpGroup {
 #pragma unroll
                         for (int i = 0; i < m; i++) a2[i] = fma(sm.Tu[l * LDm + i], a_l, a2[i]);
                     }
-#pragma unroll
-                    for (int i = 0; i < n; i++) Qxxc[i] += a1[i];
-#pragma unroll
-                    for (int i = 0; i < m; i++) Quxc[i] += a2[i];
                 }
                 if (j < m) {
-                    double a3[m];
-#pragma unroll
-                    for (int i = 0; i < m; i++) a3[i] = 0.0;
 #pragma unroll
                     for (int l = 0; l < n; l++) {
                         const double b_l = AB[l * LDZ + n + j];
 #pragma unroll
                         for (int i = 0; i < m; i++) a3[i] = fma(sm.Tu[l * LDm + i], b_l, a3[i]);
                     }
+                }
+                tick(2);
+                // the knot's own cost / constraint expansion (independent of S: evaluated only now, so its registers are not
+                // live during the two matrix phases), then Q += the S terms
+                if (store_mode && k >= stored_from) {
+                    q_load(k);
+                } else {
+                    const int rc = P.knot_row_count[k], lo = P.knot_lam_off[k];
+                    const bool staged = (rc <= LAMCAP);
+                    expansion(k, sm.xu, staged ? sm.lam : ws + L.LAM + lo, staged ? sm.mu : ws + L.MU + lo);
+                }
+                if (j < n) {
+                    Qx_j += accA;
+#pragma unroll
+                    for (int i = 0; i < n; i++) Qxxc[i] += a1[i];
+#pragma unroll
+                    for (int i = 0; i < m; i++) Quxc[i] += a2[i];
+                }
+                if (j < m) {
+                    Qu_j += accB;
 #pragma unroll
                     for (int i = 0; i < m; i++) Quuc[i] += a3[i];
                 }
