@@ -357,6 +357,9 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
     // (a warp per problem) instead of G at a time
     const unsigned int tail_threshold = v.cand_slots;  // 0: tail mode off
     unsigned int known_active = (unsigned int)s->B;  // upper bound (the list only shrinks), refreshed LAG ticks late
+    // backward pass: below this many live problems the CTA-per-problem kernel (latency path) replaces the lane-group kernel
+    unsigned int cta_threshold = (unsigned int)v.grids.bp_cta;
+    if (const char* env = getenv("TRAJOPT_B200_BP_CTA_THRESHOLD")) cta_threshold = (unsigned int)strtoul(env, nullptr, 10);
     // diagnostics: TRAJOPT_B200_TICK_LOG=<file> records one event per tick and writes "tick ms active" lines
     const char* tick_log = getenv("TRAJOPT_B200_TICK_LOG");
     const bool collect = tick_log || s->phase_timing;  // one CUDA event per phase (or per tick) on the solve stream
@@ -410,7 +413,15 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
         const int cur = (int)(t & 1);
         v.ki->ls_launch(LS_PHASE_JAC, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
         mark();
-        v.ki->ls_launch(c.o.opts_uncon.square_root ? LS_PHASE_BP_SQRT : LS_PHASE_BP, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+        const bool bp_cta = !c.o.opts_uncon.square_root && known_active <= cta_threshold;
+        if (bp_cta) {
+            // latency path: knot-parallel expansion, then one CTA per problem for the recursion
+            v.ki->ls_launch(LS_PHASE_EXPAND, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+            v.ki->ls_launch(LS_PHASE_BP_CTA, v.grids, st, v.P, Bt, c, v.lc, cur, (int)std::min<unsigned int>(known_active, (unsigned int)v.grids.bp_cta));
+            s->launches += 1;
+        } else {
+            v.ki->ls_launch(c.o.opts_uncon.square_root ? LS_PHASE_BP_SQRT : LS_PHASE_BP, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+        }
         mark();
         const bool tail = (known_active <= tail_threshold && ntrial <= 32);
         LsCtl lct = v.lc;

@@ -54,7 +54,7 @@ __host__ __device__ inline WsLayout ws_layout(int N, int Ptot, bool candidates =
     // 32 candidate trajectories of the parallel line search (persistent engine only)
     L.XB = o;  o += candidates ? (unsigned long long)N * C::n * 32 : 0ull;
     L.UB = o;  o += candidates ? (unsigned long long)(N - 1) * C::m * 32 : 0ull;
-    L.QST = o; o += (unsigned long long)(N - 1) * C::QS;
+    L.QST = o; o += (unsigned long long)N * C::QS;  // slot N-1: terminal expansion (lockstep CTA pass)
     L.CB = o;  o += 2ull * N;
     L.total = (o + 15ull) & ~15ull;
     return L;

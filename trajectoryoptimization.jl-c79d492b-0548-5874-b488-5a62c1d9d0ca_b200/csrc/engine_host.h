@@ -95,13 +95,14 @@ struct LsCtl {
     int cand_by_problem;           // 1: slot = problem id (bulk buffer), 0: slot = position in the active list (tail buffer)
 };
 
-enum { LS_PHASE_INIT = 0, LS_PHASE_JAC, LS_PHASE_BP, LS_PHASE_TRIAL, LS_PHASE_ACCEPT, LS_PHASE_OUTER, LS_PHASE_TRIAL_ALL, LS_PHASE_BP_SQRT, LS_PHASE_ACCEPT_TAIL };
+enum { LS_PHASE_INIT = 0, LS_PHASE_JAC, LS_PHASE_BP, LS_PHASE_TRIAL, LS_PHASE_ACCEPT, LS_PHASE_OUTER, LS_PHASE_TRIAL_ALL, LS_PHASE_BP_SQRT, LS_PHASE_ACCEPT_TAIL, LS_PHASE_EXPAND, LS_PHASE_BP_CTA };
 struct LsGrids {
     int init, jac, bp, trial, accept, outer;  // grid sizes (persistent, grid-stride)
     int bp_smem, bp_groups_per_block, trial_group;
     int occ_jac, occ_bp, occ_trial;
     int jac_pc;  // partial directions per thread in the Jacobian kernel
     int jac_minb, trial_minb, bp_minb;
+    int expand, bp_cta, bp_cta_smem, occ_bp_cta;  // latency path of the backward pass (ls_expand_kernel + ls_bp_cta_kernel)
     int tab_bytes;  // dynamic shared memory of the per-block copy of the knot tables / constraint rows  // __launch_bounds__ min-blocks variants (register caps)
 };
 

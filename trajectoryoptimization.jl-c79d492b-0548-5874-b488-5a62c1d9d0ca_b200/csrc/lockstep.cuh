@@ -731,6 +731,15 @@ struct BpGroup {
             for (int i = 0; i < m; i++) q[n + m + n * n + j * m + i] = Quuc[i];
         }
     }
+    // terminal knot (slot N-1 of the Q trajectory; written by ls_expand_kernel for the CTA-per-problem pass): Qx, Qxx only
+    __device__ void q_store_term(int k) {
+        double* q = ws + L.QST + (size_t)k * C::QS;
+        if (j < n) {
+            q[j] = Qx_j;
+#pragma unroll
+            for (int i = 0; i < n; i++) q[n + m + j * n + i] = Qxxc[i];
+        }
+    }
     __device__ void q_load(int k) {
         const double* q = ws + L.QST + (size_t)k * C::QS;
         if (j < n) {
@@ -749,7 +758,7 @@ struct BpGroup {
 
     // isposdef(Hermitian(A)): the arithmetic of Solver::chol_pd without its early exit (a failed pivot makes the
     // later entries NaN, which nobody reads; only the verdict is used)
-    __device__ bool chol_pd(const double* Areg) {
+    __device__ static bool chol_pd(const double* Areg) {
         double Uc[m * m];
         bool pd = true;
 #pragma unroll
@@ -775,7 +784,7 @@ struct BpGroup {
         int piv[m];
         bool tril_only, triu;
     };
-    __device__ void lu_factor(LU& f) {  // same code as Solver::lu_factor (Julia's dense `\`)
+    __device__ static void lu_factor(LU& f) {  // same code as Solver::lu_factor (Julia's dense `\`)
         bool tril = true, triu = true;
 #pragma unroll
         for (int c = 0; c < m; c++)
@@ -836,7 +845,7 @@ struct BpGroup {
             for (int i = c + 1; i < m; i++) f.a[c * m + i] = f.a[c * m + i] * rp;
         }
     }
-    __device__ void lu_solve(const LU& f, double* bv) {
+    __device__ static void lu_solve(const LU& f, double* bv) {
         if (f.tril_only) {
 #pragma unroll
             for (int i = 0; i < m; i++) {
@@ -1169,6 +1178,321 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) ls_bp_kernel(const DevProble
                 st->winner = -1;
                 st->bp_fail = ok ? 0 : 1;
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward pass, latency path: ONE CTA per problem (ls_expand_kernel + ls_bp_cta_kernel)
+//
+// With few live problems (the tail of a batch: a handful of problems that need > 1,500 iLQR
+// iterations) the lane-owns-column pass above is a chain of ~3,000 dependent warp instructions per
+// knot.  Here every OUTPUT ELEMENT of the knot's products gets its own thread, so the chain per
+// knot is a few 13-long FMA chains plus the (inherently serial) 4x4 factorisation.  The arithmetic
+// per element is the same expression as in BpGroup::run (sequential FMA chains from index 0, same
+// order of the additions), so the result is bitwise the same; only the assignment to threads differs.
+//
+// The cost / constraint expansion does not depend on the cost-to-go, so it is knot-parallel:
+// ls_expand_kernel evaluates it for every (problem, knot) with the lane-group code of BpGroup and
+// writes it to the Q trajectory (slot N-1 = terminal knot).  The recursion then ALWAYS loads Q[k]
+// from that trajectory -- which also reproduces the restart quirk Q1 (the reference accumulates
+// into Q[k] in place, backward_pass.jl:30-36): a restarted pass finds the accumulated blocks of the
+// knots it already visited and the fresh expansion everywhere else.
+// ------------------------------------------------------------------------------------------
+template <class C, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) ls_expand_kernel(const DevProblem Pg, const DevCtl ctl, const LsCtl lc, const int cur) {
+    constexpr int GS = ls_group_size<C>();
+    constexpr int GPB = (32 / GS) * WARPS;
+    constexpr int n = C::n, m = C::m;
+    extern __shared__ __align__(16) unsigned char ls_smem_raw[];
+    DevProblem P = Pg;
+    ls_stage_problem(P, Pg, ls_smem_raw + (size_t)GPB * ls_bp_stride<C>());
+    BpSmem<C>& smem_g = *reinterpret_cast<BpSmem<C>*>(ls_smem_raw + (size_t)(threadIdx.x / GS) * ls_bp_stride<C>());
+    const int N = P.N;
+    const unsigned long long total = (unsigned long long)lc.counts[cur] * (unsigned long long)N;
+    const int g = threadIdx.x / GS, j = threadIdx.x % GS;
+    const int lane = threadIdx.x & 31;
+    const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << (lane - j));
+    const bool al_on = (ctl.mode == 1);
+    for (unsigned long long it0 = (unsigned long long)blockIdx.x * GPB; it0 < total; it0 += (unsigned long long)gridDim.x * GPB) {
+        const unsigned long long it = it0 + g;
+        if (it < total) {
+            const unsigned int a = (unsigned int)(it / N);
+            const int k = (int)(it % N);
+            const int b = lc.list[cur][a];
+            TOiLQROptions io = ctl.o.opts_uncon;
+            BpGroup<C> G(P, smem_g, lc.ws + (size_t)b * lc.ws_stride, j, gmask, al_on, io);
+            G.load_cost_constants();
+            const double* xk = G.ws + G.L.X + (size_t)k * n;
+            __syncwarp(gmask);  // the group is done with the previous item's [x;u]
+            if (k < N - 1) {
+                const double* uk = G.ws + G.L.U + (size_t)k * m;
+                for (int e = j; e < n + m; e += GS) smem_g.xu[e] = (e < n) ? xk[e] : uk[e - n];
+            } else {
+                for (int e = j; e < n; e += GS) smem_g.xu[e] = xk[e];
+            }
+            __syncwarp(gmask);
+            const int lo = P.knot_lam_off[k];
+            G.expansion(k, smem_g.xu, G.ws + G.L.LAM + lo, G.ws + G.L.MU + lo);
+            if (k < N - 1) G.q_store(k);
+            else G.q_store_term(k);
+        }
+    }
+}
+
+template <class C>
+struct alignas(16) BpCtaSmem {
+    static constexpr int n = C::n, m = C::m;
+    static constexpr int LDn = (n + 1) & ~1, LDm = (m + 1) & ~1;
+    static constexpr int QSP = (C::QS + 1) & ~1;
+    // per-knot inputs, double-buffered (cp.async of knot k-1 runs during knot k)
+    double AB[2][C::ZA];   // row l = [A(l,:) B(l,:)], row length C::LDZ
+    double Q[2][QSP];      // [Qx | Qu | Qxx (col-major) | Quu | Qux] of the knot (the QST layout)
+    double S[n * LDn];     // cost-to-go S(l,j) at [j*LDn+l]
+    double Sp[n * LDn];    // unsymmetrised S
+    double T[n * LDn];     // T(i,l) = (A'S)(i,l) at [l*LDn+i]
+    double Tu[n * LDm];    // Tu(i,l) = (B'S)(i,l) at [l*LDm+i]
+    double Qxx[n * LDn];   // (i,j) at [j*LDn+i]
+    double Qux[n * LDm];   // (i,j) at [j*LDm+i]
+    double K[n * LDm];     // (i,j) at [j*LDm+i]
+    double KQ[m * LDn];    // (K'Quu)(i,c) at [c*LDn+i]
+    double Quu[m * m], Qx[n], Qu[m], d[m], Sx[n], accA[n], accB[m];
+    int pd;
+};
+
+template <class C, int NT>
+__global__ void __launch_bounds__(NT) ls_bp_cta_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
+    constexpr int n = C::n, m = C::m, LDZ = C::LDZ;
+    constexpr int LDn = BpCtaSmem<C>::LDn, LDm = BpCtaSmem<C>::LDm;
+    typedef typename BpGroup<C>::LU LU;
+    extern __shared__ __align__(16) unsigned char ls_smem_raw[];
+    BpCtaSmem<C>& sm = *reinterpret_cast<BpCtaSmem<C>*>(ls_smem_raw);
+    const int N = P.N;
+    const WsLayout L = ws_layout<C>(N, P.Ptot, false);
+    const int tid = threadIdx.x;
+    const unsigned int na = lc.counts[cur];
+    const TOiLQROptions io = ctl.o.opts_uncon;
+    for (unsigned int a = blockIdx.x; a < na; a += gridDim.x) {
+        const int b = lc.list[cur][a];
+        LsState* st = &lc.st[b];
+        double* ws = lc.ws + (size_t)b * lc.ws_stride;
+        double rho = st->rho, drho = st->drho;  // uniform over the CTA
+        auto reg_update = [&](bool increase) {  // ilqr_methods.jl:164-176
+            const double f = io.bp_reg_increase_factor;
+            if (increase) {
+                drho = dmax(drho * f, f);
+                rho = dmax(rho * drho, io.bp_reg_min);
+            } else {
+                drho = dmin(drho / f, 1.0 / f);
+                rho = rho * drho * ((rho * drho > io.bp_reg_min) ? 1.0 : 0.0);
+            }
+        };
+        auto prefetch = [&](int k, int buf) {
+            const double* ab = ws + L.Z + (size_t)k * C::ZA;  // 16-byte aligned, C::ZA even
+            for (int e = 2 * tid; e < C::ZA; e += 2 * NT) cp_async16(&sm.AB[buf][e], ab + e);
+            const double* q = ws + L.QST + (size_t)k * C::QS;
+            for (int e = tid; e < C::QS; e += NT) cp_async8(&sm.Q[buf][e], q + e);
+        };
+        bool store_mode = false, ok = true;
+        double dV0 = 0.0, dV1 = 0.0;  // kept by thread NT-1
+        for (;;) {
+            cp_async_wait_all();  // no copy of an abandoned attempt may land after the ones issued below
+            __syncthreads();      // everybody is done with the previous attempt / problem
+            prefetch(N - 2, (N - 2) & 1);
+            {   // terminal cost-to-go: S = Qxx_N, Sx = Qx_N
+                const double* qt = ws + L.QST + (size_t)(N - 1) * C::QS;
+                for (int e = tid; e < n * n; e += NT) sm.S[(e / n) * LDn + (e % n)] = qt[n + m + e];
+                for (int e = tid; e < n; e += NT) sm.Sx[e] = qt[e];
+            }
+            dV0 = 0.0;
+            dV1 = 0.0;
+            bool failed = false;
+            for (int k = N - 2; k >= 0; k--) {
+                const int buf = k & 1;
+                cp_async_wait_all();
+                __syncthreads();  // knot k's inputs have landed; S, Sx of knot k+1 are complete
+                if (k > 0) prefetch(k - 1, buf ^ 1);
+                const double* AB = sm.AB[buf];
+                const double* Qk = sm.Q[buf];
+                // ---- step 1: T = A'S, Tu = B'S, A'Sx, B'Sx (one output element per thread)
+                for (int t = tid; t < n * n + m * n + n + m; t += NT) {
+                    if (t < n * n) {
+                        const int i = t % n, j = t / n;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < n; l++) acc = fma(AB[l * LDZ + i], sm.S[j * LDn + l], acc);
+                        sm.T[j * LDn + i] = acc;
+                    } else if (t < n * n + m * n) {
+                        const int e = t - n * n, i = e % m, j = e / m;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < n; l++) acc = fma(AB[l * LDZ + n + i], sm.S[j * LDn + l], acc);
+                        sm.Tu[j * LDm + i] = acc;
+                    } else if (t < n * n + m * n + n) {
+                        const int j = t - n * n - m * n;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < n; l++) acc = fma(AB[l * LDZ + j], sm.Sx[l], acc);
+                        sm.accA[j] = acc;
+                    } else {
+                        const int j = t - n * n - m * n - n;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < n; l++) acc = fma(AB[l * LDZ + n + j], sm.Sx[l], acc);
+                        sm.accB[j] = acc;
+                    }
+                }
+                __syncthreads();
+                // ---- step 2: Q = Q[k] + (T*A, Tu*A, Tu*B, A'Sx, B'Sx); restart mode writes the sums back (quirk Q1)
+                double* qg = ws + L.QST + (size_t)k * C::QS;
+                for (int t = tid; t < n * n + m * n + m * m + n + m; t += NT) {
+                    if (t < n * n) {
+                        const int i = t % n, j = t / n;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < n; l++) acc = fma(sm.T[l * LDn + i], AB[l * LDZ + j], acc);
+                        const double v = Qk[n + m + t] + acc;
+                        sm.Qxx[j * LDn + i] = v;
+                        if (store_mode) qg[n + m + t] = v;
+                    } else if (t < n * n + m * n) {
+                        const int e = t - n * n, i = e % m, j = e / m;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < n; l++) acc = fma(sm.Tu[l * LDm + i], AB[l * LDZ + j], acc);
+                        const double v = Qk[n + m + n * n + m * m + e] + acc;
+                        sm.Qux[j * LDm + i] = v;
+                        if (store_mode) qg[n + m + n * n + m * m + e] = v;
+                    } else if (t < n * n + m * n + m * m) {
+                        const int e = t - n * n - m * n, i = e % m, j = e / m;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < n; l++) acc = fma(sm.Tu[l * LDm + i], AB[l * LDZ + n + j], acc);
+                        const double v = Qk[n + m + n * n + e] + acc;
+                        sm.Quu[j * m + i] = v;
+                        if (store_mode) qg[n + m + n * n + e] = v;
+                    } else if (t < n * n + m * n + m * m + n) {
+                        const int j = t - n * n - m * n - m * m;
+                        const double v = Qk[j] + sm.accA[j];
+                        sm.Qx[j] = v;
+                        if (store_mode) qg[j] = v;
+                    } else {
+                        const int j = t - n * n - m * n - m * m - n;
+                        const double v = Qk[n + j] + sm.accB[j];
+                        sm.Qu[j] = v;
+                        if (store_mode) qg[n + j] = v;
+                    }
+                }
+                __syncthreads();
+                // ---- step 3: Quu_reg = Quu + rho*I: PD test (warp 1) beside the LU factorisation and the solves for K, d (warp 0)
+                if (tid <= n) {
+                    LU f;
+#pragma unroll
+                    for (int e = 0; e < m * m; e++) f.a[e] = sm.Quu[e];
+#pragma unroll
+                    for (int i = 0; i < m; i++) f.a[i * m + i] = sm.Quu[i * m + i] + rho * 1.0;
+                    BpGroup<C>::lu_factor(f);
+                    double rhs[m];
+#pragma unroll
+                    for (int i = 0; i < m; i++) rhs[i] = (tid < n) ? sm.Qux[tid * LDm + i] : sm.Qu[i];
+                    BpGroup<C>::lu_solve(f, rhs);
+                    if (tid < n) {
+                        double Kc[m];
+#pragma unroll
+                        for (int i = 0; i < m; i++) {
+                            Kc[i] = -1.0 * rhs[i];
+                            sm.K[tid * LDm + i] = Kc[i];
+                        }
+#pragma unroll
+                        for (int c = 0; c < m; c++) {  // KQ = K'Quu (row tid)
+                            double acc = 0.0;
+#pragma unroll
+                            for (int l = 0; l < m; l++) acc = fma(Kc[l], sm.Quu[c * m + l], acc);
+                            sm.KQ[c * LDn + tid] = acc;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < m; i++) sm.d[i] = -1.0 * rhs[i];
+                    }
+                } else if (tid == 32) {
+                    double A_[m * m];
+#pragma unroll
+                    for (int e = 0; e < m * m; e++) A_[e] = sm.Quu[e];
+#pragma unroll
+                    for (int i = 0; i < m; i++) A_[i * m + i] = sm.Quu[i * m + i] + rho * 1.0;
+                    sm.pd = BpGroup<C>::chol_pd(A_) ? 1 : 0;
+                }
+                __syncthreads();
+                if (!sm.pd) { failed = true; break; }
+                // ---- step 4: gains out, unsymmetrised cost-to-go, dV
+                {
+                    double* kd = ws + L.KD + (size_t)k * C::KDS;
+                    for (int t = tid; t < n * n + n + m * n + m + 1; t += NT) {
+                        if (t < n * n) {  // S.xx(i,j) = Qxx + KQ*K + K'Qux + Qux'K
+                            const int i = t % n, j = t / n;
+                            double b1 = 0.0, b2 = 0.0, b3 = 0.0;
+#pragma unroll
+                            for (int l = 0; l < m; l++) {
+                                const double k_l = sm.K[j * LDm + l], q_l = sm.Qux[j * LDm + l];
+                                b1 = fma(sm.KQ[l * LDn + i], k_l, b1);
+                                b2 = fma(sm.K[i * LDm + l], q_l, b2);
+                                b3 = fma(sm.Qux[i * LDm + l], k_l, b3);
+                            }
+                            sm.Sp[j * LDn + i] = ((sm.Qxx[j * LDn + i] + b1) + b2) + b3;
+                        } else if (t < n * n + n) {  // S.x = Qx + KQ d + K'Qu + Qux'd
+                            const int j = t - n * n;
+                            double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                            for (int l = 0; l < m; l++) a1 = fma(sm.KQ[l * LDn + j], sm.d[l], a1);
+#pragma unroll
+                            for (int l = 0; l < m; l++) a2 = fma(sm.K[j * LDm + l], sm.Qu[l], a2);
+#pragma unroll
+                            for (int l = 0; l < m; l++) a3 = fma(sm.Qux[j * LDm + l], sm.d[l], a3);
+                            sm.Sx[j] = ((sm.Qx[j] + a1) + a2) + a3;
+                        } else if (t < n * n + n + m * n) {
+                            const int e = t - n * n - n;  // kd[j*m+i] = K(i,j)
+                            kd[e] = sm.K[(e / m) * LDm + (e % m)];
+                        } else if (t < n * n + n + m * n + m) {
+                            const int i = t - n * n - n - m * n;
+                            kd[m * n + i] = sm.d[i];
+                        }
+                    }
+                    if (tid == NT - 1) {  // dV
+                        double a_ = 0.0;
+#pragma unroll
+                        for (int l = 0; l < m; l++) a_ = fma(sm.d[l], sm.Qu[l], a_);
+                        dV0 += a_;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int c = 0; c < m; c++) {
+                            double w = 0.0;
+#pragma unroll
+                            for (int l = 0; l < m; l++) w = fma(0.5 * sm.d[l], sm.Quu[c * m + l], w);
+                            acc = fma(w, sm.d[c], acc);
+                        }
+                        dV1 += acc;
+                    }
+                }
+                __syncthreads();
+                // ---- step 5: symmetrise
+                for (int t = tid; t < n * n; t += NT) {
+                    const int i = t % n, j = t / n;
+                    sm.S[j * LDn + i] = 0.5 * (sm.Sp[j * LDn + i] + sm.Sp[i * LDn + j]);
+                }
+            }
+            if (!failed) break;
+            if (!store_mode) {  // first failure: replay the pass keeping the accumulated blocks
+                store_mode = true;
+                continue;
+            }
+            if (!isfinite(rho)) { ok = false; break; }
+            reg_update(true);
+        }
+        cp_async_wait_all();
+        if (ok) reg_update(false);
+        if (tid == NT - 1) {
+            st->rho = rho; st->drho = drho; st->dV0 = dV0; st->dV1 = dV1;
+            st->winner = -1;
+            st->bp_fail = ok ? 0 : 1;
         }
     }
 }
@@ -1755,6 +2079,12 @@ template <class C> LsTrialFn ls_trial_variant(int minb, bool all) {
     return all ? ls_trial_kernel<C, 32, 3> : ls_trial_kernel<C, LS_TRIAL_G, 3>;
 }
 
+template <class C> constexpr int ls_bp_cta_threads() {
+    // one thread per element of the largest per-knot product set (n*n + m*n + m*m + n + m), rounded to warps, within 64..256
+    constexpr int need = C::n * C::n + C::m * C::n + C::m * C::m + C::n + C::m;
+    return need > 192 ? 256 : (need > 128 ? 192 : (need > 64 ? 128 : 64));
+}
+
 template <class C> unsigned long long ls_ws_doubles_fn(int N, int Ptot) { return ws_layout<C>(N, Ptot, false).total; }
 
 template <class C> int ls_setup_fn(int sm_count, int N, int nrows, LsGrids* g) {
@@ -1796,6 +2126,15 @@ template <class C> int ls_setup_fn(int sm_count, int N, int nrows, LsGrids* g) {
     g->occ_trial = nb;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_accept_kernel<C>, 64, 0);
     g->accept = sm_count * (nb > 0 ? nb : 1);
+    // latency path of the backward pass: expansion kernel (lane groups, same block shape as ls_bp_kernel) + CTA per problem
+    if (cudaFuncSetAttribute(ls_expand_kernel<C, LS_BP_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->bp_smem) != cudaSuccess) return -4;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_expand_kernel<C, LS_BP_WARPS>, 32 * LS_BP_WARPS, g->bp_smem);
+    g->expand = sm_count * (nb > 0 ? nb : 1);
+    g->bp_cta_smem = (int)sizeof(BpCtaSmem<C>);
+    if (cudaFuncSetAttribute(ls_bp_cta_kernel<C, ls_bp_cta_threads<C>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->bp_cta_smem) != cudaSuccess) return -5;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_bp_cta_kernel<C, ls_bp_cta_threads<C>()>, ls_bp_cta_threads<C>(), g->bp_cta_smem);
+    g->occ_bp_cta = nb;
+    g->bp_cta = sm_count * (nb > 0 ? nb : 1);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
@@ -1805,6 +2144,8 @@ template <class C> void ls_launch_fn(int phase, const LsGrids& g, cudaStream_t s
         case LS_PHASE_INIT: ls_init_kernel<C><<<g.init, 32, 0, st>>>(P, B, c, lc); break;
         case LS_PHASE_JAC: ls_jac_variant<C>(g.jac_pc, g.jac_minb)<<<g.jac, 128, 0, st>>>(P, lc, cur); break;
         case LS_PHASE_BP: ls_bp_variant<C>(g.bp_minb)<<<g.bp, 32 * LS_BP_WARPS, g.bp_smem, st>>>(P, c, lc, cur); break;
+        case LS_PHASE_EXPAND: ls_expand_kernel<C, LS_BP_WARPS><<<grp > 0 ? grp : g.expand, 32 * LS_BP_WARPS, g.bp_smem, st>>>(P, c, lc, cur); break;
+        case LS_PHASE_BP_CTA: ls_bp_cta_kernel<C, ls_bp_cta_threads<C>()><<<grp > 0 ? grp : g.bp_cta, ls_bp_cta_threads<C>(), g.bp_cta_smem, st>>>(P, c, lc, cur); break;
         case LS_PHASE_BP_SQRT: ls_bp_sqrt_kernel<C><<<g.accept, 64, 0, st>>>(P, c, lc, cur); break;
         case LS_PHASE_TRIAL: ls_trial_variant<C>(g.trial_minb, false)<<<g.trial, 128, g.tab_bytes, st>>>(P, B, c, lc, cur, grp); break;
         case LS_PHASE_TRIAL_ALL: ls_trial_variant<C>(g.trial_minb, true)<<<g.trial, 128, g.tab_bytes, st>>>(P, B, c, lc, cur, 0); break;
