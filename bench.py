@@ -337,8 +337,9 @@ def main():
             roofline = {
                 "bound": "fp64", "achieved": ach_tf, "peak": fp64.value, "unit": "TFLOP/s", "frac": ach_tf / fp64.value if fp64.value > 0 else None,
                 "traffic": (traffic_pp * passes / launches_bp) if traffic_pp else None,
-                "kernel": "tob::ls_bp_kernel<Cfg<4,0,false,false,2>,4,3> (backward pass; %.0f%% of the device time of a step)" % (
-                    100.0 * bp_ms / max(1e-9, float(phase_ms.sum()))),
+                "kernel": "backward-pass phase: tob::ls_bp_kernel<Cfg<4,0,false,false,2>,4,3> (16 lanes per problem; ticks with > 4,096 live "
+                          "problems) and tob::ls_expand_kernel + tob::ls_bp_cta_kernel<..,256,2> (CTA per problem; the other ticks); "
+                          "%.0f%% of the device time of a step" % (100.0 * bp_ms / max(1e-9, float(phase_ms.sum()))),
                 "peak_source": "measured register-resident DFMA probe (to_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; "
                                "tensor cores do not apply (13x13 FP64 contractions)",
                 "launches": int(launches_bp), "avg_launch_ms": bp_ms / launches_bp,

@@ -179,9 +179,16 @@ function marshal(prob::TO.Problem)
 end
 
 # ---- options ------------------------------------------------------------------------------------------
-c_opts(o::TO.iLQRSolverOptions) = TOiLQROptions(o.cost_tolerance, o.gradient_norm_tolerance, o.iterations, o.dJ_counter_limit,
+# bp_reg_type / gradient_type: only the reference defaults (:control, :todorov) are on the device path (no test, benchmark or
+# example of the reference sets anything else); refuse the others instead of silently ignoring them
+function check_fixed(o::TO.iLQRSolverOptions)
+    o.bp_reg_type == :control || error("TrajOptB200: bp_reg_type=$(o.bp_reg_type) is not on the device path (only :control)")
+    o.gradient_type == :todorov || error("TrajOptB200: gradient_type=$(o.gradient_type) is not on the device path (only :todorov)")
+    o
+end
+c_opts(o::TO.iLQRSolverOptions) = (check_fixed(o); TOiLQROptions(o.cost_tolerance, o.gradient_norm_tolerance, o.iterations, o.dJ_counter_limit,
     o.square_root, o.iterations_linesearch, o.line_search_lower_bound, o.line_search_upper_bound, o.bp_reg_increase_factor,
-    o.bp_reg_max, o.bp_reg_min, o.bp_reg_fp, o.max_cost_value, o.max_state_value, o.max_control_value)
+    o.bp_reg_max, o.bp_reg_min, o.bp_reg_fp, o.max_cost_value, o.max_state_value, o.max_control_value))
 c_opts(o::TO.AugmentedLagrangianSolverOptions) = TOALOptions(c_opts(o.opts_uncon), o.cost_tolerance, o.cost_tolerance_intermediate,
     o.gradient_norm_tolerance, o.gradient_norm_tolerance_intermediate, o.constraint_tolerance, o.iterations,
     o.kickout_max_penalty, o.dual_min, o.dual_max, o.penalty_max, o.penalty_initial, o.penalty_scaling)

@@ -73,13 +73,42 @@ def test_parity_small_batches(to, oracle, name):
 @pytest.mark.parametrize("name", ["quad_altro", "quad_regdiv", "cart_altro", "escape_notebook", "park_inf_altro", "pend_mintime",
                                   "acrobot_sqrt_al"])
 def test_parity_grouped_line_search(to, oracle, name, monkeypatch):
-    """the same engine with tail mode off: step sizes tried 8 at a time with retry lists (the bulk path of large batches)"""
+    """the same engine with the bulk kernels of large batches forced on: step sizes tried 8 at a time with retry lists, and the
+    lane-group backward pass (ls_bp_kernel) instead of the CTA-per-problem one that small batches get by default"""
     monkeypatch.setenv("TRAJOPT_B200_TAIL_THRESHOLD", "0")
+    monkeypatch.setenv("TRAJOPT_B200_BP_CTA_THRESHOLD", "0")
     B = 8
     prob, opts, x0, X0 = CASES[name](B)
     ref = oracle.solve(prob, opts, x0=x0, X0=X0, B=B, inner_cap=2048, outer_cap=96)
     gpu = _solve_gpu(to, prob, opts, x0, X0, B)
     _compare(ref, gpu, B)
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if c not in ("escape_altro",)])
+def test_parity_lane_group_backward_pass(to, oracle, name, monkeypatch):
+    """every case through ls_bp_kernel (16 lanes per problem, the bulk backward pass) with the tail-mode line search"""
+    monkeypatch.setenv("TRAJOPT_B200_BP_CTA_THRESHOLD", "0")
+    B = 8
+    prob, opts, x0, X0 = CASES[name](B)
+    ref = oracle.solve(prob, opts, x0=x0, X0=X0, B=B, inner_cap=2048, outer_cap=96)
+    gpu = _solve_gpu(to, prob, opts, x0, X0, B)
+    _compare(ref, gpu, B)
+
+
+def test_backward_pass_kernels_agree_bitwise(to, monkeypatch):
+    """the two backward-pass kernels (lane group per problem / CTA per problem with the knot-parallel expansion) on a batch
+    that has regularisation restarts and a REG_DIVERGED problem: identical result records, X and U"""
+    B = 256
+    prob, opts, x0, _ = CASES["quad_altro"](B)
+    x0 = x0.copy()
+    pr, _, xr, _ = CASES["quad_regdiv"](8)
+    x0[:8] = xr
+    monkeypatch.setenv("TRAJOPT_B200_BP_CTA_THRESHOLD", "0")
+    a = _solve_gpu(to, prob, opts, x0, None, B, inner_cap=0, outer_cap=0)
+    monkeypatch.setenv("TRAJOPT_B200_BP_CTA_THRESHOLD", "100000000")
+    b = _solve_gpu(to, prob, opts, x0, None, B, inner_cap=0, outer_cap=0)
+    assert a["results"].tobytes() == b["results"].tobytes()
+    assert np.array_equal(a["X"], b["X"], equal_nan=True) and np.array_equal(a["U"], b["U"], equal_nan=True)
 
 
 @pytest.mark.parametrize("name", ["di_altro", "quad_altro", "quad_regdiv", "cart_ilqr", "escape_notebook", "park_inf_altro", "pend_mintime"])

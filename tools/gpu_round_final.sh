@@ -17,4 +17,8 @@ echo "ncu launches exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'ls_(jac|bp|trial|accept_tail)_kernel' -s 12 -c 6 -f -o $OUT/${TAG}_prof \
     python bench.py --batch 8192 --steps 1 --warmup 0 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu full exit $?"
+# the latency path of the backward pass (expansion kernel + CTA per problem): one tick with 1,024 live problems
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'ls_(expand|bp_cta)_kernel' -s 10 -c 2 -f -o $OUT/${TAG}_prof_cta \
+    python bench.py --batch 1024 --steps 1 --warmup 0 --no-cpu-baseline > $OUT/${TAG}_ncu_full_cta.log 2>&1
+echo "ncu full (cta) exit $?"
 ls -la $OUT | tail -8

@@ -1,0 +1,81 @@
+"""Run every BASELINE.json config at its full batch size on the GPU (they are parity cases, not bench lines) and check a
+spread sample of each batch against the CPU oracle, bit for bit.  One JSON line per config; the collected lines go to
+gpurun_out/<tag>_configs.json.  Usage on the GPU box:  python tools/run_configs.py [tag] [scale]
+(scale divides every batch size, e.g. 8 for a quick pass)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import trajopt_b200 as to  # noqa: E402
+from trajopt_b200 import api  # noqa: E402
+import oracle_py  # noqa: E402
+from cases import CASES  # noqa: E402
+
+# (BASELINE.json config, case name, batch, oracle sample size)
+CONFIGS = [
+    ("configs[0] README block move", "di_altro", 1, 1),
+    ("configs[1] pendulum iLQR", "pend_ilqr", 4096, 16),
+    ("configs[1] cartpole iLQR", "cart_ilqr", 4096, 16),
+    ("configs[2] quadrotor ALTRO", "quad_altro", 65536, 8),
+    ("configs[3] car_escape infeasible ALTRO", "escape_altro", 16384, 4),
+    ("configs[3] parallel_park infeasible ALTRO", "park_inf_altro", 16384, 8),
+    ("configs[4] acrobot sqrt + min-time ALTRO", "acrobot_sqrt_mintime", 32768, 8),
+    ("configs[4] doublependulum sqrt + min-time ALTRO", "dp_sqrt_mintime", 32768, 8),
+]
+
+
+def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else "configs"
+    scale = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    only = sys.argv[3:]
+    out = []
+    for label, name, B, ns in CONFIGS:
+        if only and name not in only:
+            continue
+        B = max(1, B // scale)
+        prob, opts, x0, X0 = CASES[name](B)
+        bs = api.BatchSolver(prob, B, 0, 0, 0)
+        try:
+            U0 = np.broadcast_to(prob.U, (B,) + prob.U.shape)
+            bs.set_batch(x0, U0, X0)
+            bs.solve(opts)          # warm-up (allocations, first launches)
+            bs.set_batch(x0, U0, X0)
+            t0 = time.time()
+            bs.solve(opts)
+            wall = time.time() - t0
+            ms = bs.kernel_ms()
+            res = bs.results()
+            X, U, _ = bs.solution()
+        finally:
+            bs.close()
+        idx = np.unique(np.linspace(0, B - 1, min(ns, B)).astype(int))
+        t0 = time.time()
+        ref = oracle_py.solve(prob, opts, x0=x0[idx], X0=None if X0 is None else X0[idx], B=len(idx), inner_cap=0, outer_cap=0, want_duals=False)
+        t_cpu = time.time() - t0
+        same_rec = ref["results"].tobytes() == res[idx].tobytes()
+        same_xu = bool(np.array_equal(ref["X"], X[idx], equal_nan=True) and np.array_equal(ref["U"], U[idx], equal_nan=True))
+        st, cnt = np.unique(res["status"], return_counts=True)
+        line = {
+            "config": label, "case": name, "batch": B, "device_ms": ms, "wall_s": wall, "solves_per_s": B / (ms * 1e-3),
+            "ilqr_iters_per_s": float(res["steps"].sum()) / (ms * 1e-3), "mean_iters": float(res["steps"].mean()),
+            "status_histogram": {str(int(k)): int(v) for k, v in zip(st, cnt)},
+            "oracle_sample": [int(i) for i in idx], "oracle_cpu_s_per_problem": t_cpu / len(idx),
+            "sample_records_bit_exact": bool(same_rec), "sample_XU_bit_exact": same_xu,
+        }
+        print(json.dumps(line), flush=True)
+        out.append(line)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", tag + "_configs.json"), "w"), indent=1)
+    bad = [l["case"] for l in out if not (l["sample_records_bit_exact"] and l["sample_XU_bit_exact"])]
+    print("MISMATCH in: %s" % bad if bad else "all sampled problems bit-exact")
+
+
+if __name__ == "__main__":
+    main()

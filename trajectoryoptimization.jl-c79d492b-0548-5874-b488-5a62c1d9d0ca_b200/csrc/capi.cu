@@ -358,7 +358,9 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
     const unsigned int tail_threshold = v.cand_slots;  // 0: tail mode off
     unsigned int known_active = (unsigned int)s->B;  // upper bound (the list only shrinks), refreshed LAG ticks late
     // backward pass: below this many live problems the CTA-per-problem kernel (latency path) replaces the lane-group kernel
-    unsigned int cta_threshold = (unsigned int)v.grids.bp_cta;
+    // (measured on the quadrotor, profiles/r01q, r01r: 4,096 beats 1,184 and 296 -- the regularisation-restart chains of single
+    // problems, which stall a whole launch of the lane-group kernel, run 5x faster on the latency path)
+    unsigned int cta_threshold = 4096u;
     if (const char* env = getenv("TRAJOPT_B200_BP_CTA_THRESHOLD")) cta_threshold = (unsigned int)strtoul(env, nullptr, 10);
     // diagnostics: TRAJOPT_B200_TICK_LOG=<file> records one event per tick and writes "tick ms active" lines
     const char* tick_log = getenv("TRAJOPT_B200_TICK_LOG");

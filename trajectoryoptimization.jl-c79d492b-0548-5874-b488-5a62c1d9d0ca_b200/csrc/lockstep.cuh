@@ -1260,8 +1260,8 @@ struct alignas(16) BpCtaSmem {
     int pd;
 };
 
-template <class C, int NT>
-__global__ void __launch_bounds__(NT) ls_bp_cta_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
+template <class C, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ls_bp_cta_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
     constexpr int n = C::n, m = C::m, LDZ = C::LDZ;
     constexpr int LDn = BpCtaSmem<C>::LDn, LDm = BpCtaSmem<C>::LDm;
     typedef typename BpGroup<C>::LU LU;
@@ -2085,6 +2085,14 @@ template <class C> constexpr int ls_bp_cta_threads() {
     return need > 192 ? 256 : (need > 128 ? 192 : (need > 64 ? 128 : 64));
 }
 
+template <class C> LsBpFn ls_bp_cta_variant(int minb) {
+    if constexpr (C::MODEL == 4) {  // quadrotor: register-cap variants (occupancy of the latency path when it serves thousands of problems)
+        if (minb == 3) return ls_bp_cta_kernel<C, ls_bp_cta_threads<C>(), 3>;
+        if (minb == 4) return ls_bp_cta_kernel<C, ls_bp_cta_threads<C>(), 4>;
+    }
+    return ls_bp_cta_kernel<C, ls_bp_cta_threads<C>(), 2>;
+}
+
 template <class C> unsigned long long ls_ws_doubles_fn(int N, int Ptot) { return ws_layout<C>(N, Ptot, false).total; }
 
 template <class C> int ls_setup_fn(int sm_count, int N, int nrows, LsGrids* g) {
@@ -2131,8 +2139,12 @@ template <class C> int ls_setup_fn(int sm_count, int N, int nrows, LsGrids* g) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_expand_kernel<C, LS_BP_WARPS>, 32 * LS_BP_WARPS, g->bp_smem);
     g->expand = sm_count * (nb > 0 ? nb : 1);
     g->bp_cta_smem = (int)sizeof(BpCtaSmem<C>);
-    if (cudaFuncSetAttribute(ls_bp_cta_kernel<C, ls_bp_cta_threads<C>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->bp_cta_smem) != cudaSuccess) return -5;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_bp_cta_kernel<C, ls_bp_cta_threads<C>()>, ls_bp_cta_threads<C>(), g->bp_cta_smem);
+    g->bp_cta_minb = 2;
+    if constexpr (C::MODEL == 4) {
+        if (const char* env = getenv("TRAJOPT_B200_BP_CTA_MINB")) { const int v = atoi(env); if (v == 3 || v == 4) g->bp_cta_minb = v; }
+    }
+    if (cudaFuncSetAttribute(ls_bp_cta_variant<C>(g->bp_cta_minb), cudaFuncAttributeMaxDynamicSharedMemorySize, g->bp_cta_smem) != cudaSuccess) return -5;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_bp_cta_variant<C>(g->bp_cta_minb), ls_bp_cta_threads<C>(), g->bp_cta_smem);
     g->occ_bp_cta = nb;
     g->bp_cta = sm_count * (nb > 0 ? nb : 1);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
@@ -2145,7 +2157,7 @@ template <class C> void ls_launch_fn(int phase, const LsGrids& g, cudaStream_t s
         case LS_PHASE_JAC: ls_jac_variant<C>(g.jac_pc, g.jac_minb)<<<g.jac, 128, 0, st>>>(P, lc, cur); break;
         case LS_PHASE_BP: ls_bp_variant<C>(g.bp_minb)<<<g.bp, 32 * LS_BP_WARPS, g.bp_smem, st>>>(P, c, lc, cur); break;
         case LS_PHASE_EXPAND: ls_expand_kernel<C, LS_BP_WARPS><<<grp > 0 ? grp : g.expand, 32 * LS_BP_WARPS, g.bp_smem, st>>>(P, c, lc, cur); break;
-        case LS_PHASE_BP_CTA: ls_bp_cta_kernel<C, ls_bp_cta_threads<C>()><<<grp > 0 ? grp : g.bp_cta, ls_bp_cta_threads<C>(), g.bp_cta_smem, st>>>(P, c, lc, cur); break;
+        case LS_PHASE_BP_CTA: ls_bp_cta_variant<C>(g.bp_cta_minb)<<<grp > 0 ? grp : g.bp_cta, ls_bp_cta_threads<C>(), g.bp_cta_smem, st>>>(P, c, lc, cur); break;
         case LS_PHASE_BP_SQRT: ls_bp_sqrt_kernel<C><<<g.accept, 64, 0, st>>>(P, c, lc, cur); break;
         case LS_PHASE_TRIAL: ls_trial_variant<C>(g.trial_minb, false)<<<g.trial, 128, g.tab_bytes, st>>>(P, B, c, lc, cur, grp); break;
         case LS_PHASE_TRIAL_ALL: ls_trial_variant<C>(g.trial_minb, true)<<<g.trial, 128, g.tab_bytes, st>>>(P, B, c, lc, cur, 0); break;
