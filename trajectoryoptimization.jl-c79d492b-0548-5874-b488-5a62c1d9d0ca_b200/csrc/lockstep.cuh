@@ -203,7 +203,7 @@ struct LsSolver : Solver<C> {
 // when they are few, of the constraint rows: every knot of every live problem looks these up, and a chain of dependent
 // global loads per knot is what a latency-bound kernel can least afford.  The copy is reached through the same
 // DevProblem fields (generic pointers into shared memory).
-constexpr int LS_ROWCAP = 64;
+constexpr int LS_ROWCAP = 256;  // 14 KB of constraint rows (car_escape: ~190 distinct rows)
 __host__ __device__ inline int ls_tab_bytes(int N, int nrows) {
     const int tab = ((3 * N + 1) * 4 + 15) & ~15;
     return tab + ((nrows <= LS_ROWCAP) ? nrows * (int)sizeof(DevRow) : 0);
@@ -402,6 +402,16 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+// L1 prefetch of the 128-byte lines that hold base[0..count), spread over the `nl` lanes that call it (lane index `lane`).
+// Knots with more multipliers than the shared-memory staging holds (car_escape: 177 rows per knot) read lambda / mu from
+// global memory inside a sequential row loop; without the prefetch every row pays an L2 round trip (355 cycles per row
+// measured, profiles/r01e2), with it the loop runs out of L1.
+__device__ __forceinline__ void prefetch_span(const double* base, int count, int lane, int nl) {
+    const unsigned long long b = reinterpret_cast<unsigned long long>(base) & ~127ull;
+    const unsigned long long e = reinterpret_cast<unsigned long long>(base + count);
+    for (unsigned long long q = b + (unsigned long long)lane * 128ull; q < e; q += (unsigned long long)nl * 128ull)
+        asm volatile("prefetch.global.L1 [%0];\n" ::"l"(q));
+}
 
 template <class C>
 struct BpGroup {
@@ -523,6 +533,10 @@ struct BpGroup {
         const bool term = (k == N - 1);
         const int rb = P.knot_row_begin[k], rc = al_on ? P.knot_row_count[k] : 0;
         const bool has_al = rc > 0;
+        if (rc > LAMCAP) {  // multipliers / penalties come from global memory: fetch the knot's lines before the row loop
+            prefetch_span(lams, rc, j, GS);
+            prefetch_span(mus, rc, j, GS);
+        }
         double dxx = 0.0, duu = 0.0, ax = 0.0, au = 0.0;
 #pragma unroll
         for (int i = 0; i < n; i++) Qxxc[i] = 0.0;
@@ -1314,62 +1328,54 @@ __global__ void __launch_bounds__(NT, MINB) ls_bp_cta_kernel(const DevProblem P,
                 if (k > 0) prefetch(k - 1, buf ^ 1);
                 const double* AB = sm.AB[buf];
                 const double* Qk = sm.Q[buf];
-                // ---- step 1: T = A'S, Tu = B'S, A'Sx, B'Sx (one output element per thread)
+                // ---- step 1: T = A'S, Tu = B'S, A'Sx, B'Sx (one output element per thread).  Every task is "column c of [A B] dot a
+                // vector": one code path, selected by pointers, so the warps that hold two task kinds do not run two chains in turn
                 for (int t = tid; t < n * n + m * n + n + m; t += NT) {
+                    int c;
+                    const double* V;
+                    double* out;
                     if (t < n * n) {
                         const int i = t % n, j = t / n;
-                        double acc = 0.0;
-#pragma unroll
-                        for (int l = 0; l < n; l++) acc = fma(AB[l * LDZ + i], sm.S[j * LDn + l], acc);
-                        sm.T[j * LDn + i] = acc;
+                        c = i; V = &sm.S[j * LDn]; out = &sm.T[j * LDn + i];
                     } else if (t < n * n + m * n) {
                         const int e = t - n * n, i = e % m, j = e / m;
-                        double acc = 0.0;
-#pragma unroll
-                        for (int l = 0; l < n; l++) acc = fma(AB[l * LDZ + n + i], sm.S[j * LDn + l], acc);
-                        sm.Tu[j * LDm + i] = acc;
+                        c = n + i; V = &sm.S[j * LDn]; out = &sm.Tu[j * LDm + i];
                     } else if (t < n * n + m * n + n) {
                         const int j = t - n * n - m * n;
-                        double acc = 0.0;
-#pragma unroll
-                        for (int l = 0; l < n; l++) acc = fma(AB[l * LDZ + j], sm.Sx[l], acc);
-                        sm.accA[j] = acc;
+                        c = j; V = sm.Sx; out = &sm.accA[j];
                     } else {
                         const int j = t - n * n - m * n - n;
-                        double acc = 0.0;
-#pragma unroll
-                        for (int l = 0; l < n; l++) acc = fma(AB[l * LDZ + n + j], sm.Sx[l], acc);
-                        sm.accB[j] = acc;
+                        c = n + j; V = sm.Sx; out = &sm.accB[j];
                     }
+                    double acc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < n; l++) acc = fma(AB[l * LDZ + c], V[l], acc);
+                    *out = acc;
                 }
                 __syncthreads();
                 // ---- step 2: Q = Q[k] + (T*A, Tu*A, Tu*B, A'Sx, B'Sx); restart mode writes the sums back (quirk Q1)
                 double* qg = ws + L.QST + (size_t)k * C::QS;
                 for (int t = tid; t < n * n + m * n + m * m + n + m; t += NT) {
-                    if (t < n * n) {
-                        const int i = t % n, j = t / n;
+                    if (t < n * n + m * n + m * m) {  // "row i of T or Tu dot column c of [A B]": one code path
+                        const double* Lp;
+                        int ld, c, qi;
+                        double* out;
+                        if (t < n * n) {
+                            const int i = t % n, j = t / n;
+                            Lp = &sm.T[i]; ld = LDn; c = j; qi = n + m + t; out = &sm.Qxx[j * LDn + i];
+                        } else if (t < n * n + m * n) {
+                            const int e = t - n * n, i = e % m, j = e / m;
+                            Lp = &sm.Tu[i]; ld = LDm; c = j; qi = n + m + n * n + m * m + e; out = &sm.Qux[j * LDm + i];
+                        } else {
+                            const int e = t - n * n - m * n, i = e % m, j = e / m;
+                            Lp = &sm.Tu[i]; ld = LDm; c = n + j; qi = n + m + n * n + e; out = &sm.Quu[j * m + i];
+                        }
                         double acc = 0.0;
 #pragma unroll
-                        for (int l = 0; l < n; l++) acc = fma(sm.T[l * LDn + i], AB[l * LDZ + j], acc);
-                        const double v = Qk[n + m + t] + acc;
-                        sm.Qxx[j * LDn + i] = v;
-                        if (store_mode) qg[n + m + t] = v;
-                    } else if (t < n * n + m * n) {
-                        const int e = t - n * n, i = e % m, j = e / m;
-                        double acc = 0.0;
-#pragma unroll
-                        for (int l = 0; l < n; l++) acc = fma(sm.Tu[l * LDm + i], AB[l * LDZ + j], acc);
-                        const double v = Qk[n + m + n * n + m * m + e] + acc;
-                        sm.Qux[j * LDm + i] = v;
-                        if (store_mode) qg[n + m + n * n + m * m + e] = v;
-                    } else if (t < n * n + m * n + m * m) {
-                        const int e = t - n * n - m * n, i = e % m, j = e / m;
-                        double acc = 0.0;
-#pragma unroll
-                        for (int l = 0; l < n; l++) acc = fma(sm.Tu[l * LDm + i], AB[l * LDZ + n + j], acc);
-                        const double v = Qk[n + m + n * n + e] + acc;
-                        sm.Quu[j * m + i] = v;
-                        if (store_mode) qg[n + m + n * n + e] = v;
+                        for (int l = 0; l < n; l++) acc = fma(Lp[l * ld], AB[l * LDZ + c], acc);
+                        const double v = Qk[qi] + acc;
+                        *out = v;
+                        if (store_mode) qg[qi] = v;
                     } else if (t < n * n + m * n + m * m + n) {
                         const int j = t - n * n - m * n - m * m;
                         const double v = Qk[j] + sm.accA[j];
@@ -1505,6 +1511,7 @@ template <class C>
 TOB_DEV double knot_al_cost_at(const DevProblem& P, int k, const double* lamk, const double* muk, const double* x, const double* u) {
     const int rb = P.knot_row_begin[k], rc = P.knot_row_count[k];
     double t1 = 0.0, t2 = 0.0;
+#pragma unroll 4
     for (int i = 0; i < rc; i++) {
         const DevRow r = P.rows[rb + i];
         const double c = row_value<C>(r, x, u);
@@ -1546,11 +1553,15 @@ struct Rollout {
             for (int e = t; e < SS; e += nact) cp_async8(dst + e, (e < n) ? (xk + e) : ((e < n + m) ? (uk + (e - n)) : (kd + (e - n - m))));
             if (al_on) {
                 const int rc = P.knot_row_count[k], lo = P.knot_lam_off[k];
-                if (rc <= LC)
+                if (rc <= LC) {
                     for (int e = t; e < rc; e += nact) {
                         cp_async8(dst + SS + e, lam + lo + e);
                         cp_async8(dst + SS + LC + e, mu + lo + e);
                     }
+                } else {  // too many for the staging buffer: the row loop reads global memory, one knot ahead into L1
+                    prefetch_span(lam + lo, rc, t, nact);
+                    prefetch_span(mu + lo, rc, t, nact);
+                }
             }
         };
         double xb[n], ub[m];
