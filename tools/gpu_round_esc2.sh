@@ -1,0 +1,12 @@
+#!/bin/bash
+# candidate-layout change: parity + quad tick timing; ncu source-level capture of the car_escape line-search kernel (tail mode)
+TAG=${1:-r01e4}
+OUT=gpurun_out
+mkdir -p $OUT
+timeout 600 python tools/gpu_diag.py > $OUT/${TAG}_diag.log 2>&1; tail -1 $OUT/${TAG}_diag.log
+TRAJOPT_B200_TAIL_THRESHOLD=0 timeout 600 python tools/gpu_diag.py quad_altro quad_regdiv cart_altro escape_notebook park_inf_altro > $OUT/${TAG}_diag_grouped.log 2>&1; tail -1 $OUT/${TAG}_diag_grouped.log
+TRAJOPT_B200_TICK_DETAIL=1 TRAJOPT_B200_TICK_LOG=$OUT/${TAG}_ticks_quad.txt timeout 300 python bench.py --batch 16384 --steps 1 --warmup 0 --no-cpu-baseline > $OUT/${TAG}_bench_quad.json 2> $OUT/${TAG}_bench_quad.err
+grep 'timed step' $OUT/${TAG}_bench_quad.err; python tools/tick_summary.py $OUT/${TAG}_ticks_quad.txt
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'ls_trial_kernel' -s 300 -c 1 -f -o $OUT/${TAG}_prof_escape_trial \
+    python tools/run_configs.py ${TAG} 64 escape_altro > $OUT/${TAG}_ncu_escape.log 2>&1
+echo "ncu exit $?"

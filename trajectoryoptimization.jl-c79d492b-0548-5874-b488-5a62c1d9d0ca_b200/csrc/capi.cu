@@ -319,7 +319,7 @@ int ensure_engine_buffers(TOSolver* s, Variant& v) {
         unsigned int slots = (unsigned int)s->sm_count * 8u;
         if (const char* env = getenv("TRAJOPT_B200_TAIL_THRESHOLD")) slots = (unsigned int)atoi(env);  // 0 disables tail mode
         if (slots > (unsigned int)s->B) slots = (unsigned int)s->B;
-        const size_t per = (size_t)(N * v.ki->n + (N - 1) * v.ki->m) * 32;
+        const size_t per = (size_t)(N * v.ki->n + (N - 1) * v.ki->m) * 32;  // doubles per problem for 32 candidates (cand_span)
         if (slots > 0 && cudaMalloc(&v.cand_alloc, (size_t)slots * per * sizeof(double)) == cudaSuccess) v.cand_slots = slots;
         else { cudaGetLastError(); v.cand_alloc = nullptr; v.cand_slots = 0; }
         // bulk: the G candidates of every problem (skipped if it would not leave a quarter of the device memory free)

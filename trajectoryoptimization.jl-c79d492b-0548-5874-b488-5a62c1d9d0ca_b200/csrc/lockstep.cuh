@@ -1510,11 +1510,19 @@ __global__ void __launch_bounds__(NT, MINB) ls_bp_cta_kernel(const DevProblem P,
 template <class C>
 TOB_DEV double knot_al_cost_at(const DevProblem& P, int k, const double* lamk, const double* muk, const double* x, const double* u) {
     const int rb = P.knot_row_begin[k], rc = P.knot_row_count[k];
+    if (rc == 0) return 0.0 + 0.0;
+    // z = [x;u] as a dynamically indexable (local-memory, L1-resident) array: a bound / goal / slack row reads z[col] with one
+    // load instead of walking an (n+m)-way select chain over registers (that chain was 20 % of the instructions of the
+    // quadrotor line search: 4 rows x 17 compares + selects per knot)
+    double z[C::n + C::m];
+#pragma unroll
+    for (int i = 0; i < C::n; i++) z[i] = x[i];
+#pragma unroll
+    for (int i = 0; i < C::m; i++) z[C::n + i] = u[i];
     double t1 = 0.0, t2 = 0.0;
-#pragma unroll 4
     for (int i = 0; i < rc; i++) {
         const DevRow r = P.rows[rb + i];
-        const double c = row_value<C>(r, x, u);
+        const double c = BpGroup<C>::row_value_s(r, z);
         const double l = lamk[i];
         const bool act = r.eq ? true : ((c >= 0.0) || (l > 0.0));
         const double am = act ? muk[i] : 0.0;
@@ -1523,6 +1531,14 @@ TOB_DEV double knot_al_cost_at(const DevProblem& P, int k, const double* lamk, c
     }
     return t1 + t2;
 }
+
+// Candidate trajectories of the line search: CW step sizes of one problem share a buffer, interleaved element by element
+// (element e of candidate `col` at e*CW + col), so the lanes of a problem write each element as one contiguous segment.
+// (Measured alternative, profiles/r01e4: interleaving in 32-byte units makes the accept kernel's single-candidate read use whole
+// sectors -- accept 0.68 -> 0.65 ms per 16,384 problems -- but turns every rollout store into partial-sector writes: line search
+// 3.17 -> 3.54 ms.  Kept element-wise.)
+__host__ __device__ __forceinline__ size_t cand_index(size_t e, int col, int CW) { return e * (size_t)CW + (size_t)col; }
+__host__ __device__ __forceinline__ size_t cand_span(size_t count, int CW) { return count * (size_t)CW; }  // doubles for `count` elements
 
 template <class C>
 struct RolloutStage {
@@ -1598,9 +1614,9 @@ struct Rollout {
             }
             if (CAND) {
 #pragma unroll
-                for (int i = 0; i < n; i++) XB[((size_t)k * n + i) * CW + slot] = xb[i];
+                for (int i = 0; i < n; i++) XB[cand_index((size_t)k * n + i, slot, CW)] = xb[i];
 #pragma unroll
-                for (int i = 0; i < m; i++) UB[((size_t)k * m + i) * CW + slot] = ub[i];
+                for (int i = 0; i < m; i++) UB[cand_index((size_t)k * m + i, slot, CW)] = ub[i];
             }
             double xn[n];
             {
@@ -1634,7 +1650,7 @@ struct Rollout {
             if (al_on) Jc += knot_al_cost<C>(P, N - 1, lam, mu, xb, uz);
             if (CAND) {
 #pragma unroll
-                for (int i = 0; i < n; i++) XB[((size_t)(N - 1) * n + i) * CW + slot] = xb[i];
+                for (int i = 0; i < n; i++) XB[cand_index((size_t)(N - 1) * n + i, slot, CW)] = xb[i];
             }
         }
         __syncwarp(amask);  // nobody reads the staging buffers any more
@@ -1696,9 +1712,9 @@ struct Rollout {
             }
             if (CAND) {
 #pragma unroll
-                for (int i = 0; i < n; i++) XB[((size_t)k * n + i) * CW + slot] = xb[i];
+                for (int i = 0; i < n; i++) XB[cand_index((size_t)k * n + i, slot, CW)] = xb[i];
 #pragma unroll
-                for (int i = 0; i < m; i++) UB[((size_t)k * m + i) * CW + slot] = ub[i];
+                for (int i = 0; i < m; i++) UB[cand_index((size_t)k * m + i, slot, CW)] = ub[i];
             }
             double xn[n];
             // dyn_eval (augmented model)
@@ -1738,7 +1754,7 @@ struct Rollout {
             }
             if (CAND) {
 #pragma unroll
-                for (int i = 0; i < n; i++) XB[((size_t)(N - 1) * n + i) * CW + slot] = xb[i];
+                for (int i = 0; i < n; i++) XB[cand_index((size_t)(N - 1) * n + i, slot, CW)] = xb[i];
             }
         }
         Jt = al_on ? (J + Jc) : J;
@@ -1789,9 +1805,9 @@ __global__ void __launch_bounds__(128, MINB) ls_trial_kernel(const DevProblem Pg
             if (lc.cand != nullptr) {
                 // keep every candidate of this group: G-way interleaved, slot = problem id (bulk) or list position (tail),
                 // column = step size within the group; the accept kernel copies the winner instead of re-rolling it
-                const size_t per = (size_t)(P.N * C::n + (P.N - 1) * C::m) * G;
+                const size_t per = cand_span((size_t)P.N * C::n, G) + cand_span((size_t)(P.N - 1) * C::m, G);
                 double* XB = lc.cand + (size_t)(lc.cand_by_problem ? (unsigned int)b : a0) * per;
-                double* UB = XB + (size_t)P.N * C::n * G;
+                double* UB = XB + cand_span((size_t)P.N * C::n, G);
                 ok = Rollout<C>::template run_staged<true, G>(P, io, ws, L, x0, alpha, al_on, Jt, XB, UB, t, stg, t, nact, amask);
             } else {
                 ok = Rollout<C>::template run_staged<false, G>(P, io, ws, L, x0, alpha, al_on, Jt, nullptr, nullptr, 0, stg, t, nact, amask);
@@ -1856,12 +1872,12 @@ __global__ void __launch_bounds__(32) ls_accept_tail_kernel(const DevProblem P, 
                 err = (Jres > J_prev);
                 if (!err && !(Jres > s.io.max_cost_value)) {
                     const int W = lc.cand_width, col = w % W;
-                    const size_t per = (size_t)(N * C::n + (N - 1) * C::m) * W;
-                    const double* XB = lc.cand + (size_t)(lc.cand_by_problem ? (unsigned int)b : a) * per;
-                    const double* UB = XB + (size_t)N * C::n * W;
                     const int nx = N * C::n, nu = (N - 1) * C::m;
-                    for (int e = lane; e < nx; e += 32) s.ws[s.L.X + e] = XB[(size_t)e * W + col];
-                    for (int e = lane; e < nu; e += 32) s.ws[s.L.U + e] = UB[(size_t)e * W + col];
+                    const size_t per = cand_span((size_t)nx, W) + cand_span((size_t)nu, W);
+                    const double* XB = lc.cand + (size_t)(lc.cand_by_problem ? (unsigned int)b : a) * per;
+                    const double* UB = XB + cand_span((size_t)nx, W);
+                    for (int e = lane; e < nx; e += 32) s.ws[s.L.X + e] = XB[cand_index((size_t)e, col, W)];
+                    for (int e = lane; e < nu; e += 32) s.ws[s.L.U + e] = UB[cand_index((size_t)e, col, W)];
                     __syncwarp();
                 }
             } else {
