@@ -197,6 +197,11 @@ const char *to_last_error(TOHandle h); /* h may be NULL: error of the last faile
 int to_set_batch(TOHandle h, const double *x0, const double *U0, const double *X0);
 /* Same, but the pointers are DEVICE pointers already in problem-major layout (no H2D copy). */
 int to_set_batch_device(TOHandle h, const double *x0, const double *U0, const double *X0);
+/* MPC re-solve without leaving the device (north_star "MPC initial conditions"; the reference's own tools for it are
+ * initial_controls!(prob, U), src/problem.jl:149-150, and solver reset!): the initial controls of the next solve become the
+ * last solution shifted by `shift` knots, U0[k] = U[min(k + shift, N-2)]; the initial states are x0 (host, B x n) or, when x0 is
+ * NULL, the states the last plan predicts, X[shift].  Workspaces, kernels and streams of the handle are reused. */
+int to_warm_start_shift(TOHandle h, const double *x0, int32_t shift);
 
 /* Trace capacity per problem (0 = no histories).  Must be set before solving. */
 int to_set_trace(TOHandle h, int32_t inner_capacity, int32_t outer_capacity);

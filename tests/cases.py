@@ -117,6 +117,27 @@ def _park(B):
     return p, park_options(), x0, None
 
 
+def _car_3obs(B):
+    """problems/car_3obs.jl with the ALTRO options of examples/IROS_2019/car_3obs.jl:10-27 (projected Newton off: the AL phase
+    stops at the tolerance altro_methods.jl:6-9 would hand it, 1e-3)"""
+    p = problems.car_3obs()
+    al = api.AugmentedLagrangianSolverOptions(cost_tolerance=1e-4, cost_tolerance_intermediate=1e-2, constraint_tolerance=1e-3,
+                                              penalty_scaling=50.0, penalty_initial=10.0)
+    return p, api.ALTROSolverOptions(opts_al=al), problems.batch_x0("car_3obs", B), None
+
+
+def _quad_obs(B):
+    """problems/quad_obs.jl with the AL options of examples/quadrotor/quad_obs.jl:85-95 (cylinders = circle rows, spheres =
+    sphere rows, state + control bounds with infinite entries trimmed)"""
+    p = problems.quad_obs()
+    il = api.iLQRSolverOptions(iterations=300)
+    al = api.AugmentedLagrangianSolverOptions(opts_uncon=il, iterations=25, cost_tolerance=1e-5, cost_tolerance_intermediate=1e-3,
+                                              constraint_tolerance=1e-4, penalty_scaling=10.0, penalty_initial=0.1)
+    x0 = problems.batch_x0("quadrotor", B)
+    x0[0] = p.x0
+    return p, al, x0, None
+
+
 def _pend_mintime(B):
     """test/minimum_time_tests.jl:17-19,38-46 (pendulum, R_minimum_time=15, dt_max=0.15)"""
     p = problems.pendulum()
@@ -181,6 +202,8 @@ CASES = {
     "escape_notebook": _escape_notebook,
     "park_altro": _park,
     "park_inf_altro": _park_inf,
+    "car_3obs_altro": _car_3obs,
+    "quad_obs_al": _quad_obs,
     "pend_mintime": _pend_mintime,
     "pend_rk4_altro": _pend_integrator("rk4"),
     "pend_midpoint_altro": _pend_integrator("midpoint"),

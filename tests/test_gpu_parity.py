@@ -195,6 +195,44 @@ def test_reference_integration_inequalities(to):
     assert np.abs(p_mt.X[-1] - p_mt.xf).max() < 1e-3 and to.max_violation(p_mt) < o.opts_al.constraint_tolerance
 
 
+def test_mpc_warm_start_shift(to, oracle):
+    """to_warm_start_shift: the re-solve from the device-side shifted controls equals (bit for bit) a fresh solve that is handed
+    the same shifted controls and predicted states through to_set_batch, matches the oracle on them, and needs fewer iLQR
+    iterations than the cold solve did."""
+    B = 16
+    prob, opts, x0, _ = CASES["cart_altro"](B)
+    N, n, m = prob.N, prob.model.n, prob.model.m
+    bs = to.api.BatchSolver(prob, B, 0, 0, 0)
+    try:
+        bs.set_batch(x0, np.broadcast_to(prob.U, (B, N - 1, m)))
+        bs.solve(opts)
+        cold = bs.results().copy()
+        X, U, _ = bs.solution()
+        X, U = X.copy(), U.copy()
+        bs.warm_start_shift(None, 1)
+        bs.solve(opts)
+        warm = bs.results().copy()
+        Xw, Uw, _ = bs.solution()
+        Xw, Uw = Xw.copy(), Uw.copy()
+    finally:
+        bs.close()
+    U0 = np.concatenate([U[:, 1:], U[:, -1:]], axis=1)
+    x1 = X[:, 1]
+    fresh = to.api.BatchSolver(prob, B, 0, 0, 0)
+    try:
+        fresh.set_batch(x1, U0)
+        fresh.solve(opts)
+        rf = fresh.results().copy()
+        Xf, Uf, _ = fresh.solution()
+        assert rf.tobytes() == warm.tobytes() and np.array_equal(Xf, Xw) and np.array_equal(Uf, Uw)
+    finally:
+        fresh.close()
+    p2 = prob.copy()
+    ref = oracle.solve(p2, opts, x0=x1[:4], U0=U0[:4], B=4, inner_cap=0, outer_cap=0)
+    assert ref["results"].tobytes() == warm[:4].tobytes() and np.array_equal(ref["X"], Xw[:4])
+    assert warm["steps"].sum() < cold["steps"].sum()
+
+
 def test_batched_solve_matches_singles_and_is_order_independent(to):
     """The new batched solve!: B problems at once == B single solves (queue order must not matter)."""
     B = 64

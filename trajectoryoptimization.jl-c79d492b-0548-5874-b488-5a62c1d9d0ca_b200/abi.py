@@ -82,7 +82,7 @@ class TOOuterRecord(C.Structure):
 # every symbol include/trajopt_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "to_default_ilqr_options", "to_default_al_options", "to_default_altro_options", "to_create", "to_destroy",
-    "to_last_error", "to_set_batch", "to_set_batch_device", "to_set_trace", "to_solve_ilqr", "to_solve_al",
+    "to_last_error", "to_set_batch", "to_set_batch_device", "to_warm_start_shift", "to_set_trace", "to_solve_ilqr", "to_solve_al",
     "to_solve_altro", "to_solve_altro_async", "to_sync", "to_last_kernel_ms", "to_last_launch_count",
     "to_get_solution", "to_get_results", "to_results_device_ptr", "to_get_trace", "to_num_constraint_rows",
     "to_get_duals", "to_stream", "to_copy_results_device", "to_last_linesearch_trials", "to_measure_fp64_peak",
@@ -115,6 +115,7 @@ def load_library(path=None):
     lib.to_last_error.restype = C.c_char_p
     lib.to_set_batch.argtypes = [vp, vp, vp, vp]
     lib.to_set_batch_device.argtypes = [vp, vp, vp, vp]
+    lib.to_warm_start_shift.argtypes = [vp, vp, C.c_int32]
     lib.to_set_trace.argtypes = [vp, C.c_int32, C.c_int32]
     lib.to_solve_ilqr.argtypes = [vp, C.POINTER(TOiLQROptions)]
     lib.to_solve_al.argtypes = [vp, C.POINTER(TOALOptions)]
@@ -135,7 +136,7 @@ def load_library(path=None):
     lib.to_measure_fp64_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     lib.to_device_count.restype = C.c_int
     lib.to_version.restype = C.c_char_p
-    for name in ["to_set_batch", "to_set_batch_device", "to_set_trace", "to_solve_ilqr", "to_solve_al", "to_solve_altro",
+    for name in ["to_set_batch", "to_set_batch_device", "to_warm_start_shift", "to_set_trace", "to_solve_ilqr", "to_solve_al", "to_solve_altro",
                  "to_solve_altro_async", "to_sync", "to_last_kernel_ms", "to_last_launch_count", "to_get_solution",
                  "to_get_results", "to_results_device_ptr", "to_get_trace", "to_num_constraint_rows", "to_get_duals",
                  "to_stream", "to_copy_results_device", "to_last_linesearch_trials", "to_measure_fp64_peak"]:

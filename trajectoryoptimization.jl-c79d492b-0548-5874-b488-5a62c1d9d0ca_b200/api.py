@@ -495,6 +495,13 @@ class BatchSolver:
         self._check(self.lib.to_set_batch(self.h, self._x0.ctypes.data, self._U0.ctypes.data,
                                           None if self._X0 is None else self._X0.ctypes.data))
 
+    def warm_start_shift(self, x0=None, shift=1):
+        """MPC re-solve on the resident workspaces: next initial controls = the last solution shifted by `shift` knots (last
+        control repeated); next initial states = `x0` (B x n, e.g. the measured states) or the plan's own X[shift]."""
+        if x0 is not None:
+            self._x0 = np.ascontiguousarray(np.broadcast_to(np.asarray(x0, dtype=np.float64).reshape(-1, self.n), (self.B, self.n)))
+        self._check(self.lib.to_warm_start_shift(self.h, None if x0 is None else self._x0.ctypes.data, int(shift)))
+
     def solve(self, opts):
         mode, o = as_altro_options(opts)
         if mode == 0:

@@ -714,6 +714,37 @@ int to_set_batch_device(TOHandle s, const double* x0, const double* U0, const do
     return set_batch_impl(s, x0, U0, X0, cudaMemcpyDeviceToDevice);
 }
 
+// MPC warm start on the device: the next solve's initial controls are the last solution shifted by `shift` knots (the last
+// control repeated), its initial state is x0 (host, B x n) or, if x0 is NULL, the state the last plan predicts at knot `shift`.
+__global__ void warm_start_shift_kernel(double* U0, double* x0, const double* U, const double* X, int B, int N, int n, int m, int shift,
+                                        int take_x) {
+    const size_t per = (size_t)(N - 1) * m;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)B * per; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = e / per, r = e % per;
+        const int k = (int)(r / m), i = (int)(r % m);
+        const int ks = (k + shift < N - 1) ? (k + shift) : (N - 2);
+        U0[e] = U[b * per + (size_t)ks * m + i];
+    }
+    if (take_x)
+        for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)B * n; e += (size_t)gridDim.x * blockDim.x)
+            x0[e] = X[(e / n) * (size_t)N * n + (size_t)shift * n + (e % n)];
+}
+
+int to_warm_start_shift(TOHandle s, const double* x0, int32_t shift) {
+    if (!s) return TO_ERR_INVALID;
+    if (!s->batch_set || !s->X || !s->U) return s->fail(TO_ERR_INVALID, "to_warm_start_shift: no previous solve on this handle");
+    if (shift < 0 || shift > s->d.N - 1) return s->fail(TO_ERR_INVALID, "to_warm_start_shift: shift outside [0, N-1]");
+    CK_RET(s, cudaSetDevice(s->device));
+    const int n = s->d.n, m = s->d.m, N = s->d.N, B = s->B;
+    if (x0) CK_RET(s, cudaMemcpyAsync(s->x0, x0, (size_t)B * n * 8, cudaMemcpyHostToDevice, s->stream));
+    const size_t total = (size_t)B * (N - 1) * m;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)s->sm_count * 16);
+    warm_start_shift_kernel<<<grid, 256, 0, s->stream>>>(s->U0, s->x0, s->U, s->X, B, N, n, m, shift, x0 ? 0 : 1);
+    CK_RET(s, cudaGetLastError());
+    s->has_X0 = false;  // a warm start is a feasible start (the rollout of the shifted controls)
+    return 0;
+}
+
 int to_set_trace(TOHandle s, int32_t inner_capacity, int32_t outer_capacity) {
     if (!s || inner_capacity < 0 || outer_capacity < 0) return TO_ERR_INVALID;
     CK_RET(s, cudaSetDevice(s->device));

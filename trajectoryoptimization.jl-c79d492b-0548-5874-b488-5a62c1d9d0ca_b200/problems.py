@@ -163,6 +163,59 @@ def parallel_park(infeasible=False):
     return api.Problem(model, obj, constraints=cons, x0=x0, xf=xf, N=N, dt=dt, U0=np.ones((N - 1, m)), X0=X0)
 
 
+def car_3obs():
+    """problems/car_3obs.jl: car past three circular obstacles (circle_constraint rows at 1<k<N), goal at N."""
+    model = api.rk3(api.Dynamics.car)
+    n, m, N, dt = 3, 2, 101, 0.05
+    x0, xf = np.zeros(n), np.array([1.0, 1.0, 0.0])
+    obj = api.LQRObjective(_eye(n, 1.0), _eye(m, 1e-1), _eye(n, 100.0), xf, N)
+    obs = api.CircleConstraints([(0.25, 0.25, 0.1), (0.5, 0.5, 0.1), (0.75, 0.75, 0.1)], "obs")
+    cons = api.Constraints(N)
+    for k in range(1, N - 1):
+        cons.add(k, obs)
+    cons.add(N - 1, api.goal_constraint(xf))
+    return api.Problem(model, obj, constraints=cons, x0=x0, xf=xf, N=N, dt=dt, U0=np.full((N - 1, m), 0.01))
+
+
+def quad_obs():
+    """problems/quad_obs.jl: quadrotor among 4 cylinders and 3 spheres with state + control bounds.  Two things the file does
+    are kept as they are: `sphere_constraint(x, s[1], s[2], s[3], s[3] + r_quad)` takes the sphere's z as its radius (the tuples'
+    fourth entry is unused), and `initial_controls!(quadrotor, U_hover)` initialises the OTHER problem, so quad_obs starts from
+    U = 0 (problems/quad_obs.jl:69-70,86)."""
+    model = api.rk3(api.Dynamics.quadrotor)
+    n, m, N = 13, 4, 101
+    dt = 5.0 / (N - 1)
+    x0 = np.zeros(n)
+    x0[0:3] = [0.0, 0.0, 10.0]
+    x0[3] = 1.0
+    xf = np.zeros(n)
+    xf[0:3] = [0.0, 60.0, 10.0]
+    xf[3] = 1.0
+    obj = api.LQRObjective(_eye(n, 1e-3), _eye(m, 1e-2), _eye(n, 1.0), xf, N)
+    x_max, x_min = np.full(n, np.inf), np.full(n, -np.inf)
+    x_max[0:3] = [25.0, np.inf, 20.0]
+    x_min[0:3] = [-25.0, -np.inf, 0.0]
+    bnd_u = api.BoundConstraint(n, m, u_min=0.0, u_max=50.0)
+    bnd = api.BoundConstraint(n, m, u_min=0.0, u_max=50.0, x_min=x_min, x_max=x_max)
+    xU, xL = xf.copy(), xf.copy()
+    xU[3:7], xL[3:7] = np.inf, -np.inf
+    xU[7:10], xL[7:10] = 0.0, 0.0
+    bnd_xf = api.BoundConstraint(n, m, x_min=xL, x_max=xU)
+    r_quad = 2.0
+    cyl = api.CircleConstraints([(0.0, 10.0, 3.0 + r_quad), (10.0, 30.0, 3.0 + r_quad), (-13.0, 25.0, 2.0 + r_quad),
+                                 (5.0, 50.0, 4.0 + r_quad)], "cylinders")
+    sph = api.SphereConstraints([(0.0, 40.0, 5.0, 5.0 + r_quad), (-5.0, 15.0, 3.0, 3.0 + r_quad), (10.0, 20.0, 7.0, 7.0 + r_quad)],
+                                "spheres")
+    cons = api.Constraints(N)
+    cons.add(0, bnd_u)
+    for k in range(1, N - 1):
+        cons.add(k, bnd)
+        cons.add(k, cyl)
+        cons.add(k, sph)
+    cons.add(N - 1, bnd_xf)
+    return api.Problem(model, obj, constraints=cons, x0=x0, xf=xf, N=N, dt=dt)
+
+
 def acrobot(N=151, dt=0.01, Qs=1e-2, Rs=1e-2, Qfs=100.0):
     """problems/acrobot.jl (goal constraint at N)."""
     model = api.rk3(api.Dynamics.acrobot_model)
@@ -234,6 +287,12 @@ def batch_x0(config, B, offset=0):
         for b in range(B):
             r = splitmix_uniform(4500 + offset + b, 3)
             out[b] = [_u(r[0], -0.1, 0.1), _u(r[1], -0.05, 0.05), _u(r[2], -0.2, 0.2)]
+        return out
+    if config == "car_3obs":
+        out = np.zeros((B, 3))
+        for b in range(B):
+            r = splitmix_uniform(6000 + offset + b, 3)
+            out[b] = [_u(r[0], -0.05, 0.05), _u(r[1], -0.05, 0.05), _u(r[2], -0.1, 0.1)]
         return out
     if config in ("acrobot", "doublependulum"):
         out = np.zeros((B, 4))
