@@ -291,11 +291,15 @@ __global__ void __launch_bounds__(128, MINB) ls_jac_kernel(const DevProblem P, c
         double* ab = ws + L.Z + (size_t)k * C::ZA;
         int nrep = 1;
         if (TZ > 0 && ch == 0) {
+            // all loads issued together, combined without short-circuit: `fin = fin && isfinite(xk[i])` made the one lane per
+            // item that checks the trivial directions walk 17 DEPENDENT DRAM loads while its warp waited (36 % of the kernel's
+            // samples, profiles/r01y source view).  The values are not kept (they are re-read from L1 below): keeping 17 more
+            // registers live cost more in spills than the loads (measured, profiles/r01u)
             bool fin = true;
 #pragma unroll
-            for (int i = 0; i < C::n0; i++) fin = fin && isfinite(xk[i]);
+            for (int i = 0; i < C::n0; i++) fin = fin & isfinite(xk[i]);
 #pragma unroll
-            for (int i = 0; i < C::m0; i++) fin = fin && isfinite(uk[i]);
+            for (int i = 0; i < C::m0; i++) fin = fin & isfinite(uk[i]);
             if (fin) {
 #pragma unroll
                 for (int c = 0; c < TZ; c++)
@@ -1590,6 +1594,11 @@ struct Rollout {
             cp_async_wait_all();
             __syncwarp(amask);  // knot k has landed; every lane is done with the other buffer
             if (k + 1 < N - 1) prefetch(k + 1, (k + 1) & 1);
+            // A rollout that left the state / control box (rollout.jl:14-18 returns false there) is rejected whatever comes
+            // after: its lane only keeps serving the staging copies and barriers.  Without this the diverged lanes (about one
+            // rollout in five at the large step sizes) drag their warp through the NaN slow paths of every division and
+            // square root of the remaining knots (21 % of the kernel's samples, profiles/r01y source view).
+            if (!ok) continue;
             const double* sk = stg + (k & 1) * SBUF;
             const double* Xk = sk;
             const double* Uk = sk + n;
@@ -1642,7 +1651,7 @@ struct Rollout {
 #pragma unroll
             for (int i = 0; i < n; i++) xb[i] = xn[i];
         }
-        {
+        if (ok) {
             double uz[m];
 #pragma unroll
             for (int i = 0; i < m; i++) uz[i] = 0.0;
@@ -1876,7 +1885,10 @@ __global__ void __launch_bounds__(32) ls_accept_tail_kernel(const DevProblem P, 
                     const size_t per = cand_span((size_t)nx, W) + cand_span((size_t)nu, W);
                     const double* XB = lc.cand + (size_t)(lc.cand_by_problem ? (unsigned int)b : a) * per;
                     const double* UB = XB + cand_span((size_t)nx, W);
+                    // (unrolled: 8 independent loads in flight per lane -- the copy is a DRAM-latency chain otherwise)
+#pragma unroll 8
                     for (int e = lane; e < nx; e += 32) s.ws[s.L.X + e] = XB[cand_index((size_t)e, col, W)];
+#pragma unroll 8
                     for (int e = lane; e < nu; e += 32) s.ws[s.L.U + e] = UB[cand_index((size_t)e, col, W)];
                     __syncwarp();
                 }
