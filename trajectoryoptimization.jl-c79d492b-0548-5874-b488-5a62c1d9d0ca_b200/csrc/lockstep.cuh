@@ -290,16 +290,19 @@ __global__ void __launch_bounds__(128, MINB) ls_jac_kernel(const DevProblem P, c
         const double* uk = ws + L.U + (size_t)k * C::m;
         double* ab = ws + L.Z + (size_t)k * C::ZA;
         int nrep = 1;
-        if (TZ > 0 && ch == 0) {
-            // all loads issued together, combined without short-circuit: `fin = fin && isfinite(xk[i])` made the one lane per
-            // item that checks the trivial directions walk 17 DEPENDENT DRAM loads while its warp waited (36 % of the kernel's
-            // samples, profiles/r01y source view).  The values are not kept (they are re-read from L1 below): keeping 17 more
-            // registers live cost more in spills than the loads (measured, profiles/r01u)
-            bool fin = true;
+        // Finite check of the knot's [x;u] (only the lane with ch == 0 needs the verdict).  All loads are issued together and
+        // combined without short-circuit: `fin = fin && isfinite(xk[i])` made that one lane walk 17 DEPENDENT DRAM loads while
+        // its warp waited (36 % of the kernel's samples, profiles/r01y source view).  Every lane runs it, so the warp waits
+        // once, together, and the values every lane needs below are in L1 by then.  They are not kept in registers: 17 more
+        // live registers cost more in spills than the reloads (measured, profiles/r01u).
+        bool fin = true;
+        if (TZ > 0) {
 #pragma unroll
             for (int i = 0; i < C::n0; i++) fin = fin & isfinite(xk[i]);
 #pragma unroll
             for (int i = 0; i < C::m0; i++) fin = fin & isfinite(uk[i]);
+        }
+        if (TZ > 0 && ch == 0) {
             if (fin) {
 #pragma unroll
                 for (int c = 0; c < TZ; c++)
