@@ -298,12 +298,13 @@ int ensure_engine_buffers(TOSolver* s, Variant& v) {
         snprintf(buf, sizeof buf, "cudaMalloc of %.1f MB per-problem workspaces failed", bytes / 1048576.0);
         return s->fail(TO_ERR_NOMEM, buf);
     }
-    if (cudaMalloc(&v.lc.st, B * sizeof(LsState)) != cudaSuccess || cudaMalloc(&v.ls_lists, 5 * B * sizeof(int)) != cudaSuccess ||
+    if (cudaMalloc(&v.lc.st, B * sizeof(LsState)) != cudaSuccess || cudaMalloc(&v.ls_lists, 6 * B * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&v.lc.counts, 64) != cudaSuccess)
         return s->fail(TO_ERR_NOMEM, "cudaMalloc failed (lockstep state)");
     v.lc.list[0] = v.ls_lists; v.lc.list[1] = v.ls_lists + B;
     v.lc.retry[0] = v.ls_lists + 2 * B; v.lc.retry[1] = v.ls_lists + 3 * B;
     v.lc.outer_list = v.ls_lists + 4 * B;
+    v.lc.restart_list = v.ls_lists + 5 * B;
     int rc = v.ki->ls_setup(s->sm_count, N, v.P.nrows, &v.grids);
     if (rc != 0) {
         snprintf(buf, sizeof buf, "lockstep kernel setup failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
@@ -361,6 +362,8 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
     // (measured on the quadrotor, profiles/r01q, r01r: 4,096 beats 1,184 and 296 -- the regularisation-restart chains of single
     // problems, which stall a whole launch of the lane-group kernel, run 5x faster on the latency path)
     unsigned int cta_threshold = 4096u;
+    bool defer_restarts = true;
+    if (const char* env = getenv("TRAJOPT_B200_BP_DEFER_RESTARTS")) defer_restarts = (env[0] != '0');
     if (const char* env = getenv("TRAJOPT_B200_BP_CTA_THRESHOLD")) cta_threshold = (unsigned int)strtoul(env, nullptr, 10);
     // diagnostics: TRAJOPT_B200_TICK_LOG=<file> records one event per tick and writes "tick ms active" lines
     const char* tick_log = getenv("TRAJOPT_B200_TICK_LOG");
@@ -421,8 +424,17 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
             v.ki->ls_launch(LS_PHASE_EXPAND, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
             v.ki->ls_launch(LS_PHASE_BP_CTA, v.grids, st, v.P, Bt, c, v.lc, cur, (int)std::min<unsigned int>(known_active, (unsigned int)v.grids.bp_cta));
             s->launches += 1;
+        } else if (c.o.opts_uncon.square_root) {
+            v.ki->ls_launch(LS_PHASE_BP_SQRT, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+        } else if (defer_restarts) {
+            // bulk: the lane-group kernel serves up to LS_BP_INLINE_RESTARTS regularisation increases per problem itself and
+            // queues the rare long restart chains (restart list, zeroed by the Jacobian kernel) for the latency path
+            v.ki->ls_launch(LS_PHASE_BP, v.grids, st, v.P, Bt, c, v.lc, cur | 2, 0);
+            v.ki->ls_launch(LS_PHASE_EXPAND, v.grids, st, v.P, Bt, c, v.lc, cur | 4, 2 * s->sm_count);
+            v.ki->ls_launch(LS_PHASE_BP_CTA, v.grids, st, v.P, Bt, c, v.lc, cur | 4, 0);
+            s->launches += 2;
         } else {
-            v.ki->ls_launch(c.o.opts_uncon.square_root ? LS_PHASE_BP_SQRT : LS_PHASE_BP, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+            v.ki->ls_launch(LS_PHASE_BP, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
         }
         mark();
         const bool tail = (known_active <= tail_threshold && ntrial <= 32);

@@ -81,11 +81,12 @@ struct LsState {
     int bp_fail;                  // the backward pass of this tick aborted (TO_STATUS_REG_DIVERGED)
 };
 
-// counters: [0],[1] = sizes of the two active lists, [2],[3] = retry lists, [4] = outer list
+// counters: [0],[1] = sizes of the two active lists, [2],[3] = retry lists, [4] = outer list, [5] = restart list
 struct LsCtl {
     int* list[2];
     int* retry[2];
     int* outer_list;
+    int* restart_list;             // problems whose backward pass a bulk launch handed over to the CTA kernel (counter: counts[5])
     unsigned int* counts;
     LsState* st;
     double* ws;                    // per-PROBLEM workspaces

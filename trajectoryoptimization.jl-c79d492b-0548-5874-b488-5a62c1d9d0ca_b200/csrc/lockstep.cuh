@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(128, MINB) ls_jac_kernel(const DevProblem P, c
     constexpr int NCH = (C::PT - TZ + PC - 1) / PC;
     typedef Dual<PC> D;
     const unsigned int na = lc.counts[cur];
-    if (blockIdx.x == 0 && threadIdx.x == 0) { lc.counts[cur ^ 1] = 0; lc.counts[2] = 0; lc.counts[3] = 0; lc.counts[4] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { lc.counts[cur ^ 1] = 0; lc.counts[2] = 0; lc.counts[3] = 0; lc.counts[4] = 0; lc.counts[5] = 0; }
     const int N = P.N;
     const unsigned int per = (unsigned int)(N - 1) * NCH;
     const unsigned long long items = (unsigned long long)na * per;
@@ -905,9 +905,13 @@ struct BpGroup {
         }
     }
 
-    // the whole backward pass of one problem, including regularisation restarts
-    __device__ bool run(double& dV0, double& dV1) {
+    // the whole backward pass of one problem, including regularisation restarts.  Returns 1 = done, 0 = the regularisation
+    // diverged (TO_STATUS_REG_DIVERGED), 2 = handed over: after `max_inline` regularisation increases (>= 0) the pass gives up
+    // WITHOUT touching the solver state, and the caller queues the problem for the CTA-per-problem kernel, which replays the
+    // pass from the start five times faster per attempt -- a 38-restart chain no longer holds a whole bulk launch for 50 ms.
+    __device__ int run(double& dV0, double& dV1, int max_inline = -1) {
         const int N = P.N;
+        int nreg = 0;
         bool store_mode = false;
         int stored_from = N - 1;
         for (;;) {
@@ -1158,15 +1162,21 @@ struct BpGroup {
             }
             if (!isfinite(rho)) {
                 cp_async_wait_all();
-                return false;
+                return 0;
+            }
+            if (max_inline >= 0 && ++nreg > max_inline) {
+                cp_async_wait_all();
+                return 2;
             }
             reg_update(true);
         }
         cp_async_wait_all();
         reg_update(false);
-        return true;
+        return 1;
     }
 };
+
+constexpr int LS_BP_INLINE_RESTARTS = 2;  // regularisation increases a bulk launch serves itself before handing the problem over
 
 template <class C, int WARPS, int MINB>
 __global__ void __launch_bounds__(32 * WARPS, MINB) ls_bp_kernel(const DevProblem Pg, const DevCtl ctl, const LsCtl lc, const int cur) {
@@ -1176,7 +1186,9 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) ls_bp_kernel(const DevProble
     DevProblem P = Pg;
     ls_stage_problem(P, Pg, ls_smem_raw + (size_t)GPB * ls_bp_stride<C>());
     BpSmem<C>& smem_g = *reinterpret_cast<BpSmem<C>*>(ls_smem_raw + (size_t)(threadIdx.x / GS) * ls_bp_stride<C>());
-    const unsigned int na = lc.counts[cur];
+    // cur: bit 0 = active list, bit 1 = hand long restart chains over to the restart list (bulk launches)
+    const int max_inline = (cur & 2) ? LS_BP_INLINE_RESTARTS : -1;
+    const unsigned int na = lc.counts[cur & 1];
     const int g = threadIdx.x / GS, j = threadIdx.x % GS;
     const int lane = threadIdx.x & 31;
     const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << (lane - j));
@@ -1184,7 +1196,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) ls_bp_kernel(const DevProble
     for (unsigned int a0 = blockIdx.x * GPB; a0 < na; a0 += gridDim.x * GPB) {
         const unsigned int a = a0 + g;
         if (a < na) {
-            const int b = lc.list[cur][a];
+            const int b = lc.list[cur & 1][a];
             LsState* st = &lc.st[b];
             TOiLQROptions io = ctl.o.opts_uncon;
             BpGroup<C> G(P, smem_g, lc.ws + (size_t)b * lc.ws_stride, j, gmask, al_on, io);
@@ -1193,11 +1205,15 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) ls_bp_kernel(const DevProble
             G.load_cost_constants();
             if (ctl.debug && a == 0) G.prof = reinterpret_cast<long long*>(ctl.debug);
             double dV0, dV1;
-            const bool ok = G.run(dV0, dV1);
+            const int rc = G.run(dV0, dV1, max_inline);
             if (j == 0) {
-                st->rho = G.rho; st->drho = G.drho; st->dV0 = dV0; st->dV1 = dV1;
-                st->winner = -1;
-                st->bp_fail = ok ? 0 : 1;
+                if (rc == 2) {
+                    ls_append(lc.restart_list, &lc.counts[5], b);  // state untouched: the CTA kernel starts over from st->rho
+                } else {
+                    st->rho = G.rho; st->drho = G.drho; st->dV0 = dV0; st->dV1 = dV1;
+                    st->winner = -1;
+                    st->bp_fail = rc ? 0 : 1;
+                }
             }
         }
     }
@@ -1230,7 +1246,9 @@ __global__ void __launch_bounds__(32 * WARPS) ls_expand_kernel(const DevProblem 
     ls_stage_problem(P, Pg, ls_smem_raw + (size_t)GPB * ls_bp_stride<C>());
     BpSmem<C>& smem_g = *reinterpret_cast<BpSmem<C>*>(ls_smem_raw + (size_t)(threadIdx.x / GS) * ls_bp_stride<C>());
     const int N = P.N;
-    const unsigned long long total = (unsigned long long)lc.counts[cur] * (unsigned long long)N;
+    // cur: bit 0 = active list; bit 2 = the restart list of this tick (problems a bulk backward pass handed over)
+    const int* list = (cur & 4) ? lc.restart_list : lc.list[cur & 1];
+    const unsigned long long total = (unsigned long long)((cur & 4) ? lc.counts[5] : lc.counts[cur & 1]) * (unsigned long long)N;
     const int g = threadIdx.x / GS, j = threadIdx.x % GS;
     const int lane = threadIdx.x & 31;
     const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << (lane - j));
@@ -1240,7 +1258,7 @@ __global__ void __launch_bounds__(32 * WARPS) ls_expand_kernel(const DevProblem 
         if (it < total) {
             const unsigned int a = (unsigned int)(it / N);
             const int k = (int)(it % N);
-            const int b = lc.list[cur][a];
+            const int b = list[a];
             TOiLQROptions io = ctl.o.opts_uncon;
             BpGroup<C> G(P, smem_g, lc.ws + (size_t)b * lc.ws_stride, j, gmask, al_on, io);
             G.load_cost_constants();
@@ -1291,10 +1309,11 @@ __global__ void __launch_bounds__(NT, MINB) ls_bp_cta_kernel(const DevProblem P,
     const int N = P.N;
     const WsLayout L = ws_layout<C>(N, P.Ptot, false);
     const int tid = threadIdx.x;
-    const unsigned int na = lc.counts[cur];
+    const int* list = (cur & 4) ? lc.restart_list : lc.list[cur & 1];
+    const unsigned int na = (cur & 4) ? lc.counts[5] : lc.counts[cur & 1];
     const TOiLQROptions io = ctl.o.opts_uncon;
     for (unsigned int a = blockIdx.x; a < na; a += gridDim.x) {
-        const int b = lc.list[cur][a];
+        const int b = list[a];
         LsState* st = &lc.st[b];
         double* ws = lc.ws + (size_t)b * lc.ws_stride;
         double rho = st->rho, drho = st->drho;  // uniform over the CTA
