@@ -364,6 +364,8 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
     unsigned int cta_threshold = 4096u;
     bool defer_restarts = true;
     if (const char* env = getenv("TRAJOPT_B200_BP_DEFER_RESTARTS")) defer_restarts = (env[0] != '0');
+    int inline_restarts = LS_BP_INLINE_RESTARTS;
+    if (const char* env = getenv("TRAJOPT_B200_BP_INLINE_RESTARTS")) inline_restarts = std::max(0, std::min(64, atoi(env)));
     if (const char* env = getenv("TRAJOPT_B200_BP_CTA_THRESHOLD")) cta_threshold = (unsigned int)strtoul(env, nullptr, 10);
     // diagnostics: TRAJOPT_B200_TICK_LOG=<file> records one event per tick and writes "tick ms active" lines
     const char* tick_log = getenv("TRAJOPT_B200_TICK_LOG");
@@ -429,7 +431,7 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
         } else if (defer_restarts) {
             // bulk: the lane-group kernel serves up to LS_BP_INLINE_RESTARTS regularisation increases per problem itself and
             // queues the rare long restart chains (restart list, zeroed by the Jacobian kernel) for the latency path
-            v.ki->ls_launch(LS_PHASE_BP, v.grids, st, v.P, Bt, c, v.lc, cur | 2, 0);
+            v.ki->ls_launch(LS_PHASE_BP, v.grids, st, v.P, Bt, c, v.lc, cur | 2 | (inline_restarts << 4), 0);
             v.ki->ls_launch(LS_PHASE_EXPAND, v.grids, st, v.P, Bt, c, v.lc, cur | 4, 2 * s->sm_count);
             v.ki->ls_launch(LS_PHASE_BP_CTA, v.grids, st, v.P, Bt, c, v.lc, cur | 4, 0);
             s->launches += 2;

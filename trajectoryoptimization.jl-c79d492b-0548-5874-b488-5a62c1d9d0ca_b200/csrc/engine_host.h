@@ -96,6 +96,7 @@ struct LsCtl {
     int cand_by_problem;           // 1: slot = problem id (bulk buffer), 0: slot = position in the active list (tail buffer)
 };
 
+constexpr int LS_BP_INLINE_RESTARTS = 2;  // regularisation increases a bulk backward-pass launch serves itself before handing the problem over
 enum { LS_PHASE_INIT = 0, LS_PHASE_JAC, LS_PHASE_BP, LS_PHASE_TRIAL, LS_PHASE_ACCEPT, LS_PHASE_OUTER, LS_PHASE_TRIAL_ALL, LS_PHASE_BP_SQRT, LS_PHASE_ACCEPT_TAIL, LS_PHASE_EXPAND, LS_PHASE_BP_CTA };
 struct LsGrids {
     int init, jac, bp, trial, accept, outer;  // grid sizes (persistent, grid-stride)

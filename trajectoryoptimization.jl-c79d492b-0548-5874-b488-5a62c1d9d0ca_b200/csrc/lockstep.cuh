@@ -1176,8 +1176,6 @@ struct BpGroup {
     }
 };
 
-constexpr int LS_BP_INLINE_RESTARTS = 2;  // regularisation increases a bulk launch serves itself before handing the problem over
-
 template <class C, int WARPS, int MINB>
 __global__ void __launch_bounds__(32 * WARPS, MINB) ls_bp_kernel(const DevProblem Pg, const DevCtl ctl, const LsCtl lc, const int cur) {
     constexpr int GS = ls_group_size<C>();
@@ -1187,7 +1185,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) ls_bp_kernel(const DevProble
     ls_stage_problem(P, Pg, ls_smem_raw + (size_t)GPB * ls_bp_stride<C>());
     BpSmem<C>& smem_g = *reinterpret_cast<BpSmem<C>*>(ls_smem_raw + (size_t)(threadIdx.x / GS) * ls_bp_stride<C>());
     // cur: bit 0 = active list, bit 1 = hand long restart chains over to the restart list (bulk launches)
-    const int max_inline = (cur & 2) ? LS_BP_INLINE_RESTARTS : -1;
+    const int max_inline = (cur & 2) ? (cur >> 4) : -1;  // bits 4.. = regularisation increases served inline before the hand-over
     const unsigned int na = lc.counts[cur & 1];
     const int g = threadIdx.x / GS, j = threadIdx.x % GS;
     const int lane = threadIdx.x & 31;
