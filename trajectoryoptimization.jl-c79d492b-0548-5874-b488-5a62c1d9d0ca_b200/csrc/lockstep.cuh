@@ -1530,6 +1530,13 @@ __global__ void __launch_bounds__(NT, MINB) ls_bp_cta_kernel(const DevProblem P,
 // ------------------------------------------------------------------------------------------
 // line search: thread per (problem, step size); G consecutive lanes serve one problem
 // ------------------------------------------------------------------------------------------
+template <class C>
+struct RolloutStage {
+    static constexpr int SS = C::n + C::m + C::KDS;  // x_k, u_k, K_k, d_k
+    static constexpr int LC = 16;                    // multipliers / penalties of one knot (larger sets are read from global)
+    static constexpr int SBUF = (SS + 2 * LC + 1) & ~1;
+};
+
 // knot_al_cost with the knot's own multiplier / penalty arrays (same arithmetic as knot_al_cost in engine.cuh)
 template <class C>
 TOB_DEV double knot_al_cost_at(const DevProblem& P, int k, const double* lamk, const double* muk, const double* x, const double* u) {
@@ -1544,7 +1551,40 @@ TOB_DEV double knot_al_cost_at(const DevProblem& P, int k, const double* lamk, c
 #pragma unroll
     for (int i = 0; i < C::m; i++) z[C::n + i] = u[i];
     double t1 = 0.0, t2 = 0.0;
-    for (int i = 0; i < rc; i++) {
+    int i = 0;
+    if (rc > RolloutStage<C>::LC) {
+        // large constraint sets (car_escape: 177 rows per knot; multipliers in global memory): four rows at a time with every
+        // load issued before the first use -- the one-row-at-a-time loop paid a dependent load + branch chain of ~340 cycles
+        // per row (profiles/r01e3).  Same per-row expressions, same accumulation order.
+        for (; i + 4 <= rc; i += 4) {
+            double l4[4], m4[4], c4[4];
+            int eq4[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                l4[q] = __ldg(lamk + i + q);
+                m4[q] = __ldg(muk + i + q);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const DevRow r = P.rows[rb + i + q];
+                eq4[q] = r.eq;
+                if (r.kind == DR_CIRCLE) {  // the bulk of such sets: straight from the state registers (z lives in local memory)
+                    const double dx = x[0] - r.a, dy = x[1] - r.b;
+                    c4[q] = -(((dx * dx) + (dy * dy)) - (r.r * r.r));
+                } else {
+                    c4[q] = BpGroup<C>::row_value_s(r, z);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const bool act = eq4[q] ? true : ((c4[q] >= 0.0) || (l4[q] > 0.0));
+                const double am = act ? m4[q] : 0.0;
+                t1 = fma(l4[q], c4[q], t1);
+                t2 = fma((0.5 * c4[q]) * am, c4[q], t2);
+            }
+        }
+    }
+    for (; i < rc; i++) {
         const DevRow r = P.rows[rb + i];
         const double c = BpGroup<C>::row_value_s(r, z);
         const double l = lamk[i];
@@ -1564,12 +1604,6 @@ TOB_DEV double knot_al_cost_at(const DevProblem& P, int k, const double* lamk, c
 __host__ __device__ __forceinline__ size_t cand_index(size_t e, int col, int CW) { return e * (size_t)CW + (size_t)col; }
 __host__ __device__ __forceinline__ size_t cand_span(size_t count, int CW) { return count * (size_t)CW; }  // doubles for `count` elements
 
-template <class C>
-struct RolloutStage {
-    static constexpr int SS = C::n + C::m + C::KDS;  // x_k, u_k, K_k, d_k
-    static constexpr int LC = 16;                    // multipliers / penalties of one knot (larger sets are read from global)
-    static constexpr int SBUF = (SS + 2 * LC + 1) & ~1;
-};
 
 template <class C>
 struct Rollout {
