@@ -1557,24 +1557,24 @@ TOB_DEV double knot_al_cost_at(const DevProblem& P, int k, const double* lamk, c
         // load issued before the first use -- the one-row-at-a-time loop paid a dependent load + branch chain of ~340 cycles
         // per row (profiles/r01e3).  Same per-row expressions, same accumulation order.
         for (; i + 4 <= rc; i += 4) {
-            double l4[4], m4[4], c4[4];
-            int eq4[4];
+            double l4[4], m4[4], c4[4], ra[4], rb_[4], rr[4];
+            int eq4[4], kind4[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < 4; q++) {  // every load of the four rows first
+                const DevRow* r = &P.rows[rb + i + q];
+                kind4[q] = r->kind; eq4[q] = r->eq;
+                ra[q] = r->a; rb_[q] = r->b; rr[q] = r->r;
                 l4[q] = __ldg(lamk + i + q);
                 m4[q] = __ldg(muk + i + q);
             }
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const DevRow r = P.rows[rb + i + q];
-                eq4[q] = r.eq;
-                if (r.kind == DR_CIRCLE) {  // the bulk of such sets: straight from the state registers (z lives in local memory)
-                    const double dx = x[0] - r.a, dy = x[1] - r.b;
-                    c4[q] = -(((dx * dx) + (dy * dy)) - (r.r * r.r));
-                } else {
-                    c4[q] = BpGroup<C>::row_value_s(r, z);
-                }
+            for (int q = 0; q < 4; q++) {  // circle rows (the bulk of such sets) without a branch: four independent chains
+                const double dx = x[0] - ra[q], dy = x[1] - rb_[q];
+                c4[q] = -(((dx * dx) + (dy * dy)) - (rr[q] * rr[q]));
             }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (kind4[q] != DR_CIRCLE) c4[q] = BpGroup<C>::row_value_s(P.rows[rb + i + q], z);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const bool act = eq4[q] ? true : ((c4[q] >= 0.0) || (l4[q] > 0.0));
