@@ -96,19 +96,25 @@ def test_parity_lane_group_backward_pass(to, oracle, name, monkeypatch):
 
 
 def test_backward_pass_kernels_agree_bitwise(to, monkeypatch):
-    """the two backward-pass kernels (lane group per problem / CTA per problem with the knot-parallel expansion) on a batch
-    that has regularisation restarts and a REG_DIVERGED problem: identical result records, X and U"""
+    """the two backward-pass kernels (lane group per problem / CTA per problem with the knot-parallel expansion) and the
+    restart hand-over between them, on a batch that has regularisation restarts and a REG_DIVERGED problem: identical result
+    records, X and U"""
     B = 256
     prob, opts, x0, _ = CASES["quad_altro"](B)
     x0 = x0.copy()
     pr, _, xr, _ = CASES["quad_regdiv"](8)
     x0[:8] = xr
     monkeypatch.setenv("TRAJOPT_B200_BP_CTA_THRESHOLD", "0")
+    monkeypatch.setenv("TRAJOPT_B200_BP_DEFER_RESTARTS", "0")   # lane-group kernel serves every restart itself
     a = _solve_gpu(to, prob, opts, x0, None, B, inner_cap=0, outer_cap=0)
+    monkeypatch.setenv("TRAJOPT_B200_BP_DEFER_RESTARTS", "1")   # ... hands every regularisation increase to the CTA kernel
+    monkeypatch.setenv("TRAJOPT_B200_BP_INLINE_RESTARTS", "0")
+    c = _solve_gpu(to, prob, opts, x0, None, B, inner_cap=0, outer_cap=0)
     monkeypatch.setenv("TRAJOPT_B200_BP_CTA_THRESHOLD", "100000000")
     b = _solve_gpu(to, prob, opts, x0, None, B, inner_cap=0, outer_cap=0)
-    assert a["results"].tobytes() == b["results"].tobytes()
-    assert np.array_equal(a["X"], b["X"], equal_nan=True) and np.array_equal(a["U"], b["U"], equal_nan=True)
+    for other in (b, c):
+        assert a["results"].tobytes() == other["results"].tobytes()
+        assert np.array_equal(a["X"], other["X"], equal_nan=True) and np.array_equal(a["U"], other["U"], equal_nan=True)
 
 
 @pytest.mark.parametrize("name", ["di_altro", "quad_altro", "quad_regdiv", "cart_ilqr", "escape_notebook", "park_inf_altro", "pend_mintime"])
