@@ -1556,16 +1556,31 @@ TOB_DEV double knot_al_cost_at(const DevProblem& P, int k, const double* lamk, c
         // large constraint sets (car_escape: 177 rows per knot; multipliers in global memory): four rows at a time with every
         // load issued before the first use -- the one-row-at-a-time loop paid a dependent load + branch chain of ~340 cycles
         // per row (profiles/r01e3).  Same per-row expressions, same accumulation order.
+        // the multipliers / penalties of the NEXT block are requested before this block is computed: they come from L2
+        // (~270 cycles; the L1 prefetch does not allocate), which one block of arithmetic hides
+        double ln[4], mn[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            ln[q] = (q < rc) ? __ldg(lamk + q) : 0.0;
+            mn[q] = (q < rc) ? __ldg(muk + q) : 0.0;
+        }
         for (; i + 4 <= rc; i += 4) {
             double l4[4], m4[4], c4[4], ra[4], rb_[4], rr[4];
             int eq4[4], kind4[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { l4[q] = ln[q]; m4[q] = mn[q]; }
+            if (i + 8 <= rc) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    ln[q] = __ldg(lamk + i + 4 + q);
+                    mn[q] = __ldg(muk + i + 4 + q);
+                }
+            }
 #pragma unroll
             for (int q = 0; q < 4; q++) {  // every load of the four rows first
                 const DevRow* r = &P.rows[rb + i + q];
                 kind4[q] = r->kind; eq4[q] = r->eq;
                 ra[q] = r->a; rb_[q] = r->b; rr[q] = r->r;
-                l4[q] = __ldg(lamk + i + q);
-                m4[q] = __ldg(muk + i + q);
             }
 #pragma unroll
             for (int q = 0; q < 4; q++) {  // circle rows (the bulk of such sets) without a branch: four independent chains
