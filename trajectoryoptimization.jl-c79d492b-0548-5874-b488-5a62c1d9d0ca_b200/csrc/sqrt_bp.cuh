@@ -12,46 +12,60 @@
 
 namespace tob {
 
+// `#pragma unroll (UNR)`: the helpers are size-generic; the recursion instantiates them with UNR = UF (full unrolling for the small
+// models, whose matrices then live in registers instead of local memory), the expansion with UNR = 1 (runtime row counts)
+#define SQ_UNROLL _Pragma("unroll (UNR)")
+
 template <class C>
 struct SqrtBp {
     static constexpr int n = C::n, m = C::m, nq = C::nq, mq = C::mq, nz = C::n + C::m;
     static constexpr int PMAX = 32;                       // constraint rows per knot supported by this path
     static constexpr int RMAX = n + ((n > PMAX) ? n : PMAX);  // rows of the tallest stacked matrix
+    static constexpr int UF = (n <= 6 && m <= 6) ? 64 : 1;     // unroll factor of the recursion's helper loops
 
     // cholesky(A).U, dot-product (left-looking) form; false = not positive definite
-    template <int D>
-    static __device__ bool chol_upper(const double* A, double* U) {
+    template <int D, int UNR = 1>
+    static __device__ __forceinline__ bool chol_upper(const double* A, double* U) {
+        SQ_UNROLL
         for (int j = 0; j < D; j++) {
+            SQ_UNROLL
             for (int i = 0; i < j; i++) {
                 double acc = 0.0;
+                SQ_UNROLL
                 for (int l = 0; l < i; l++) acc = fma(U[i * D + l], U[j * D + l], acc);
                 U[j * D + i] = (A[j * D + i] - acc) / U[i * D + i];
             }
             double acc = 0.0;
+            SQ_UNROLL
             for (int l = 0; l < j; l++) acc = fma(U[j * D + l], U[j * D + l], acc);
             const double dd = A[j * D + j] - acc;
             if (!(dd > 0.0)) return false;
             U[j * D + j] = sqrt(dd);
+            SQ_UNROLL
             for (int i = j + 1; i < D; i++) U[j * D + i] = 0.0;
         }
         return true;
     }
-    template <int D>
-    static __device__ bool chol_upper_inplace(double* A) {
+    template <int D, int UNR = 1>
+    static __device__ __forceinline__ bool chol_upper_inplace(double* A) {
         double U[D * D];
+        SQ_UNROLL
         for (int e = 0; e < D * D; e++) U[e] = 0.0;
-        if (!chol_upper<D>(A, U)) return false;
+        if (!chol_upper<D, UNR>(A, U)) return false;
+        SQ_UNROLL
         for (int e = 0; e < D * D; e++) A[e] = U[e];
         return true;
     }
 
     // Householder QR of the rows×D matrix P (column-major, leading dimension `rows`), in place: R ends up in the
     // top D×D block (LAPACK dgeqr2 / dlarfg; R may have negative diagonal entries)
-    template <int D>
-    static __device__ void qr_R(double* P, int rows) {
+    template <int D, int UNR = 1>
+    static __device__ __forceinline__ void qr_R(double* P, int rows) {
+        SQ_UNROLL
         for (int j = 0; j < D && j < rows; j++) {
             const double alpha = P[j * rows + j];
             double xn2 = 0.0;
+            SQ_UNROLL
             for (int i = j + 1; i < rows; i++) xn2 = fma(P[j * rows + i], P[j * rows + i], xn2);
             double tau = 0.0;
             if (xn2 != 0.0) {
@@ -59,35 +73,45 @@ struct SqrtBp {
                 const double beta = -copysign(sqrt(alpha * alpha + xnorm * xnorm), alpha);
                 tau = (beta - alpha) / beta;
                 const double sc = 1.0 / (alpha - beta);
+                SQ_UNROLL
                 for (int i = j + 1; i < rows; i++) P[j * rows + i] = P[j * rows + i] * sc;
                 P[j * rows + j] = beta;
             }
             if (tau != 0.0) {
+                SQ_UNROLL
                 for (int c = j + 1; c < D; c++) {
                     double w = P[c * rows + j];
+                    SQ_UNROLL
                     for (int i = j + 1; i < rows; i++) w = fma(P[j * rows + i], P[c * rows + i], w);
                     const double tw = tau * w;
                     P[c * rows + j] = P[c * rows + j] - tw;
+                    SQ_UNROLL
                     for (int i = j + 1; i < rows; i++) P[c * rows + i] = fma(-tw, P[j * rows + i], P[c * rows + i]);
                 }
             }
         }
     }
     // R = qr([A; B]).R with A: D×D (upper factor, full storage), B: nb×D (leading dimension nb).  `Pbuf`: (D+nb)*D doubles
-    template <int D>
-    static __device__ void chol_plus(const double* A, const double* Bm, int nb, double* Rout, double* Pbuf) {
+    template <int D, int UNR = 1>
+    static __device__ __forceinline__ void chol_plus(const double* A, const double* Bm, int nb, double* Rout, double* Pbuf) {
         const int rows = D + nb;
+        SQ_UNROLL
         for (int j = 0; j < D; j++) {
+            SQ_UNROLL
             for (int i = 0; i < D; i++) Pbuf[j * rows + i] = A[j * D + i];
+            SQ_UNROLL
             for (int i = 0; i < nb; i++) Pbuf[j * rows + D + i] = Bm[j * nb + i];
         }
-        qr_R<D>(Pbuf, rows);
+        qr_R<D, UNR>(Pbuf, rows);
+        SQ_UNROLL
         for (int j = 0; j < D; j++)
+            SQ_UNROLL
             for (int i = 0; i < D; i++) Rout[j * D + i] = (i <= j) ? Pbuf[j * rows + i] : 0.0;
     }
     // lowrankdowndate!(Cholesky(U,:U), v); false on PosDefException
-    template <int D>
-    static __device__ bool lowrank_downdate(double* U, double* v) {
+    template <int D, int UNR = 1>
+    static __device__ __forceinline__ bool lowrank_downdate(double* U, double* v) {
+        SQ_UNROLL
         for (int i = 0; i < D; i++) {
             const double Aii = U[i * D + i];
             const double s = v[i] / Aii;
@@ -95,6 +119,7 @@ struct SqrtBp {
             if (s2 > 1.0) return false;
             const double c = sqrt(1.0 - s2);
             U[i * D + i] = c * Aii;
+            SQ_UNROLL
             for (int j = i + 1; j < D; j++) {
                 const double vj = v[j];
                 const double Aij = (U[j * D + i] - s * vj) / c;
@@ -105,15 +130,19 @@ struct SqrtBp {
         return true;
     }
     // cond(A): ratio of the extreme singular values by one-sided Jacobi (fixed sweep order)
-    template <int D>
-    static __device__ double cond2(const double* Ain) {
+    template <int D, int UNR = 1>
+    static __device__ __forceinline__ double cond2(const double* Ain) {
         double A[D * D];
+        SQ_UNROLL
         for (int e = 0; e < D * D; e++) A[e] = Ain[e];
         for (int sweep = 0; sweep < 60; sweep++) {
             double off = 0.0;
+            SQ_UNROLL
             for (int p = 0; p < D - 1; p++)
+                SQ_UNROLL
                 for (int q = p + 1; q < D; q++) {
                     double a = 0, b = 0, c = 0;
+                    SQ_UNROLL
                     for (int i = 0; i < D; i++) {
                         a = fma(A[p * D + i], A[p * D + i], a);
                         b = fma(A[q * D + i], A[q * D + i], b);
@@ -124,6 +153,7 @@ struct SqrtBp {
                     const double zeta = (b - a) / (2.0 * c);
                     const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                     const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                    SQ_UNROLL
                     for (int i = 0; i < D; i++) {
                         const double ap = A[p * D + i], aq = A[q * D + i];
                         A[p * D + i] = cs * ap - sn * aq;
@@ -133,8 +163,10 @@ struct SqrtBp {
             if (off < 1e-15) break;
         }
         double smax = 0.0, smin = __longlong_as_double(0x7ff0000000000000LL);
+        SQ_UNROLL
         for (int j = 0; j < D; j++) {
             double a = 0;
+            SQ_UNROLL
             for (int i = 0; i < D; i++) a = fma(A[j * D + i], A[j * D + i], a);
             const double sv = sqrt(a);
             smax = dmax(smax, sv);
@@ -143,37 +175,51 @@ struct SqrtBp {
         return smax / smin;
     }
     // X = U \ B and X = U' \ B for an upper-triangular D×D U, nrhs right-hand sides (column-major, ld D)
-    template <int D>
-    static __device__ void solve_upper(const double* U, const double* Bin, int nrhs, double* X) {
+    template <int D, int UNR = 1>
+    static __device__ __forceinline__ void solve_upper(const double* U, const double* Bin, int nrhs, double* X) {
+        SQ_UNROLL
         for (int c = 0; c < nrhs; c++)
+            SQ_UNROLL
             for (int i = D - 1; i >= 0; i--) {
                 double acc = 0.0;
+                SQ_UNROLL
                 for (int l = i + 1; l < D; l++) acc = fma(U[l * D + i], X[c * D + l], acc);
                 X[c * D + i] = (Bin[c * D + i] - acc) / U[i * D + i];
             }
     }
-    template <int D>
-    static __device__ void solve_upper_t(const double* U, const double* Bin, int nrhs, double* X) {
+    template <int D, int UNR = 1>
+    static __device__ __forceinline__ void solve_upper_t(const double* U, const double* Bin, int nrhs, double* X) {
+        SQ_UNROLL
         for (int c = 0; c < nrhs; c++)
+            SQ_UNROLL
             for (int i = 0; i < D; i++) {
                 double acc = 0.0;
+                SQ_UNROLL
                 for (int l = 0; l < i; l++) acc = fma(U[i * D + l], X[c * D + l], acc);
                 X[c * D + i] = (Bin[c * D + i] - acc) / U[i * D + i];
             }
     }
     // C = A'B (A: ra×ca, B: ra×cb) and C = A B (A: ra×ca, B: ca×cb), column-major
-    static __device__ void mul_AtB(const double* A, int ra, int ca, const double* Bm, int cb, double* Cm) {
+    template <int UNR = 1>
+    static __device__ __forceinline__ void mul_AtB(const double* A, int ra, int ca, const double* Bm, int cb, double* Cm) {
+        SQ_UNROLL
         for (int j = 0; j < cb; j++)
+            SQ_UNROLL
             for (int i = 0; i < ca; i++) {
                 double acc = 0.0;
+                SQ_UNROLL
                 for (int l = 0; l < ra; l++) acc = fma(A[i * ra + l], Bm[j * ra + l], acc);
                 Cm[j * ca + i] = acc;
             }
     }
-    static __device__ void mul_AB(const double* A, int ra, int ca, const double* Bm, int cb, double* Cm) {
+    template <int UNR = 1>
+    static __device__ __forceinline__ void mul_AB(const double* A, int ra, int ca, const double* Bm, int cb, double* Cm) {
+        SQ_UNROLL
         for (int j = 0; j < cb; j++)
+            SQ_UNROLL
             for (int i = 0; i < ra; i++) {
                 double acc = 0.0;
+                SQ_UNROLL
                 for (int l = 0; l < ca; l++) acc = fma(A[l * ra + i], Bm[j * ca + l], acc);
                 Cm[j * ra + i] = acc;
             }
@@ -285,15 +331,21 @@ struct SqrtBp {
 
     // The square-root backward pass of one problem.  Returns 0 = ok, 1 = restart loop diverged (TO_STATUS_REG_DIVERGED),
     // 2 = PosDefException (TO_STATUS_NOT_PD_SQRT).
+    // `pre_expanded`: ls_expand_sqrt_kernel has already written the expansion of every knot (slot N-1 = terminal knot) to the
+    // Q trajectory, one thread per (problem, knot); the serial loop below is then skipped.
     static __device__ int run(const DevProblem& P, bool al_on, const TOiLQROptions& io, double* ws, const WsLayout& L,
-                              double& rho, double& drho, double& dV0, double& dV1) {
+                              double& rho, double& drho, double& dV0, double& dV1, bool pre_expanded = false) {
         const int N = P.N;
         double Pbuf[RMAX * ((n > m) ? n : m)];
         double Sxx[n * n], Sx[n];
         // cost_expansion_sqrt! of every knot first (ilqr_methods.jl:55-62): the Q trajectory lives in global memory and
         // is updated IN PLACE by the recursion, which reproduces the reference's restart behaviour as is
         double* qst = ws + L.QST;
-        {
+        if (pre_expanded) {
+            const double* E = qst + (size_t)(N - 1) * C::QS;
+            for (int e = 0; e < n * n; e++) Sxx[e] = E[n + m + e];
+            for (int i = 0; i < n; i++) Sx[i] = E[i];
+        } else {
             double x[n], u[m], E[C::QS];
             for (int k = 0; k < N; k++) {
                 for (int i = 0; i < n; i++) x[i] = ws[L.X + (size_t)k * n + i];
@@ -323,37 +375,42 @@ struct SqrtBp {
                 for (int jj = 0; jj < n; jj++) for (int i = 0; i < n; i++) A[jj * n + i] = ab[i * C::LDZ + jj];
                 for (int jj = 0; jj < m; jj++) for (int i = 0; i < n; i++) Bm[jj * n + i] = ab[i * C::LDZ + n + jj];
             }
-            double* Q = qst + (size_t)k * C::QS;
+            // the knot's blocks are worked on in a local copy (registers for the small models) and written back once they have
+            // been updated -- before the regularisation test, so a restart finds the accumulated values (quirk Q1)
+            double* Qg = qst + (size_t)k * C::QS;
+            double Q[C::QS];
+            for (int e = 0; e < C::QS; e++) Q[e] = Qg[e];
             double* Qx = Q;
             double* Qu = Q + n;
             double* Qxx = Q + n + m;
             double* Quu = Qxx + n * n;
             double* Qux = Quu + m * m;
             double v[n], vu[m], tx[n * n], tu[n * m], Mux[m * n];
-            mul_AtB(A, n, n, Sx, 1, v);
+            mul_AtB<UF>(A, n, n, Sx, 1, v);
             for (int i = 0; i < n; i++) Qx[i] += v[i];
-            mul_AtB(Bm, n, m, Sx, 1, vu);
+            mul_AtB<UF>(Bm, n, m, Sx, 1, vu);
             for (int i = 0; i < m; i++) Qu[i] += vu[i];
-            mul_AB(Sxx, n, n, A, n, tx);
-            mul_AB(Sxx, n, n, Bm, m, tu);
+            mul_AB<UF>(Sxx, n, n, A, n, tx);
+            mul_AB<UF>(Sxx, n, n, Bm, m, tu);
             {
                 double R[n * n];
-                chol_plus<n>(Qxx, tx, n, R, Pbuf);
+                chol_plus<n, UF>(Qxx, tx, n, R, Pbuf);
                 for (int e = 0; e < n * n; e++) Qxx[e] = R[e];
             }
             {
                 double R[m * m];
-                chol_plus<m>(Quu, tu, n, R, Pbuf);
+                chol_plus<m, UF>(Quu, tu, n, R, Pbuf);
                 for (int e = 0; e < m * m; e++) Quu[e] = R[e];
             }
-            mul_AtB(tu, n, m, tx, n, Mux);
+            mul_AtB<UF>(tu, n, m, tx, n, Mux);
             for (int e = 0; e < m * n; e++) Qux[e] += Mux[e];
+            for (int e = 0; e < C::QS; e++) Qg[e] = Q[e];
             double eye[m * m], Quu_reg[m * m];
             for (int e = 0; e < m * m; e++) eye[e] = 0.0;
             const double sr = sqrt(rho);
             for (int i = 0; i < m; i++) eye[i * m + i] = sr * 1.0;
-            chol_plus<m>(Quu, eye, m, Quu_reg, Pbuf);
-            if (cond2<m>(Quu_reg) > 1e8) {
+            chol_plus<m, UF>(Quu, eye, m, Quu_reg, Pbuf);
+            if (cond2<m, UF>(Quu_reg) > 1e8) {
                 if (!isfinite(rho)) return 1;
                 const double f = io.bp_reg_increase_factor;  // regularization_update!(:increase)
                 drho = dmax(drho * f, f);
@@ -367,11 +424,11 @@ struct SqrtBp {
             }
             // K = -Quu_reg \ (Quu_reg' \ Qux) ; d likewise
             double t1[m * n], Kk[m * n], dk[m], t1d[m];
-            solve_upper_t<m>(Quu_reg, Qux, n, t1);
-            solve_upper<m>(Quu_reg, t1, n, Kk);
+            solve_upper_t<m, UF>(Quu_reg, Qux, n, t1);
+            solve_upper<m, UF>(Quu_reg, t1, n, Kk);
             for (int e = 0; e < m * n; e++) Kk[e] = -Kk[e];
-            solve_upper_t<m>(Quu_reg, Qu, 1, t1d);
-            solve_upper<m>(Quu_reg, t1d, 1, dk);
+            solve_upper_t<m, UF>(Quu_reg, Qu, 1, t1d);
+            solve_upper<m, UF>(Quu_reg, t1d, 1, dk);
             for (int i = 0; i < m; i++) dk[i] = -dk[i];
             {
                 double* kd = ws + L.KD + (size_t)k * C::KDS;
@@ -386,29 +443,29 @@ struct SqrtBp {
                     for (int l = 0; l < m; l++) acc = fma(Kk[i * m + l], Quu[l * m + jj], acc);
                     KQt[jj * n + i] = acc;
                 }
-            mul_AB(Quu, m, m, dk, 1, Qd);
-            mul_AB(KQt, n, m, Qd, 1, v1);
-            mul_AtB(Kk, m, n, Qu, 1, v2);
-            mul_AtB(Qux, m, n, dk, 1, v3);
+            mul_AB<UF>(Quu, m, m, dk, 1, Qd);
+            mul_AB<UF>(KQt, n, m, Qd, 1, v1);
+            mul_AtB<UF>(Kk, m, n, Qu, 1, v2);
+            mul_AtB<UF>(Qux, m, n, dk, 1, v3);
             double Sxk[n];
             for (int i = 0; i < n; i++) Sxk[i] = ((Qx[i] + v1[i]) + v2[i]) + v3[i];
             // tmp1 = (Q.xx') \ Q.ux'  (n×m) ; tmp2 = chol_minus(Q.uu, tmp1)
             double uxT[n * m], tmp1[n * m];
             for (int jj = 0; jj < m; jj++) for (int i = 0; i < n; i++) uxT[jj * n + i] = Qux[i * m + jj];
-            solve_upper_t<n>(Qxx, uxT, m, tmp1);
+            solve_upper_t<n, UF>(Qxx, uxT, m, tmp1);
             double U2[m * m];
             for (int e = 0; e < m * m; e++) U2[e] = Quu[e];
             for (int i = 0; i < n; i++) {
                 double rowv[m];
                 for (int jj = 0; jj < m; jj++) rowv[jj] = tmp1[jj * n + i];
-                if (!lowrank_downdate<m>(U2, rowv)) return 2;
+                if (!lowrank_downdate<m, UF>(U2, rowv)) return 2;
             }
             // S.xx = chol_plus(Q.xx + tmp1*K, tmp2*K)
             double top[n * n], bot[m * n];
-            mul_AB(tmp1, n, m, Kk, n, top);
+            mul_AB<UF>(tmp1, n, m, Kk, n, top);
             for (int e = 0; e < n * n; e++) top[e] = Qxx[e] + top[e];
-            mul_AB(U2, m, m, Kk, n, bot);
-            chol_plus<n>(top, bot, m, Sxx, Pbuf);
+            mul_AB<UF>(U2, m, m, Kk, n, bot);
+            chol_plus<n, UF>(top, bot, m, Sxx, Pbuf);
             for (int i = 0; i < n; i++) Sx[i] = Sxk[i];
             {
                 double a = 0.0;
@@ -429,6 +486,39 @@ struct SqrtBp {
     }
 };
 
+// cost_expansion_sqrt! of every knot (objective.jl:70-94, augmented_lagrangian_methods.jl:231-276): thread per (problem, knot).
+// The expansion does not depend on the cost-to-go; done here it is off the serial chain of ls_bp_sqrt_kernel (a lone problem
+// paid N expansions in sequence before its recursion started).  A knot whose stage Hessian is not positive definite (or that has
+// more rows than this path supports) flags the problem: st->bp_fail = 2, which the recursion kernel turns into NOT_PD_SQRT.
+template <class C>
+__global__ void __launch_bounds__(64) ls_expand_sqrt_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
+    constexpr int n = C::n, m = C::m;
+    const int N = P.N;
+    const unsigned long long total = (unsigned long long)lc.counts[cur] * (unsigned long long)N;
+    const WsLayout L = ws_layout<C>(N, P.Ptot, false);
+    const bool al_on = (ctl.mode == 1);
+    for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
+         it += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned int a = (unsigned int)(it / N);
+        const int k = (int)(it % N);
+        const int b = lc.list[cur][a];
+        double* ws = lc.ws + (size_t)b * lc.ws_stride;
+        double x[n], u[m], E[C::QS];
+        double Pbuf[SqrtBp<C>::RMAX * ((n > m) ? n : m)];
+        for (int i = 0; i < n; i++) x[i] = ws[L.X + (size_t)k * n + i];
+        for (int i = 0; i < m; i++) u[i] = (k < N - 1) ? ws[L.U + (size_t)k * m + i] : 0.0;
+        const int lo = P.knot_lam_off[k];
+        bool ok = !(P.knot_row_count[k] > SqrtBp<C>::PMAX && al_on);
+        if (ok) ok = SqrtBp<C>::expansion(P, al_on, k, x, u, ws + L.LAM + lo, ws + L.MU + lo, E, Pbuf);
+        if (ok) {
+            double* q = ws + L.QST + (size_t)k * C::QS;
+            for (int e = 0; e < C::QS; e++) q[e] = E[e];
+        } else {
+            lc.st[b].bp_fail = 2;
+        }
+    }
+}
+
 // thread per problem
 template <class C>
 __global__ void __launch_bounds__(64) ls_bp_sqrt_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
@@ -440,11 +530,14 @@ __global__ void __launch_bounds__(64) ls_bp_sqrt_kernel(const DevProblem P, cons
         LsState* st = &lc.st[b];
         TOiLQROptions io = ctl.o.opts_uncon;
         double rho = st->rho, drho = st->drho, dV0 = 0.0, dV1 = 0.0;
-        const int rc = SqrtBp<C>::run(P, al_on, io, lc.ws + (size_t)b * lc.ws_stride, L, rho, drho, dV0, dV1);
+        // the expansions were written by ls_expand_sqrt_kernel, which also flags a failed knot
+        const int rc = (st->bp_fail == 2) ? 2 : SqrtBp<C>::run(P, al_on, io, lc.ws + (size_t)b * lc.ws_stride, L, rho, drho, dV0, dV1, true);
         st->rho = rho; st->drho = drho; st->dV0 = dV0; st->dV1 = dV1;
         st->winner = -1;
         st->bp_fail = rc;
     }
 }
+
+#undef SQ_UNROLL
 
 }  // namespace tob
