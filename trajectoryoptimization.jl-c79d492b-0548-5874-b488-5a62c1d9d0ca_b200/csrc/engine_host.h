@@ -103,7 +103,7 @@ struct LsGrids {
     int bp_smem, bp_groups_per_block, trial_group;
     int occ_jac, occ_bp, occ_trial;
     int jac_pc;  // partial directions per thread in the Jacobian kernel
-    int jac_minb, trial_minb, bp_minb;
+    int jac_minb, trial_minb, bp_minb, trial_all_minb;
     int expand, bp_cta, bp_cta_smem, occ_bp_cta, bp_cta_minb;  // latency path of the backward pass (ls_expand_kernel + ls_bp_cta_kernel)
     int tab_bytes;  // dynamic shared memory of the per-block copy of the knot tables / constraint rows  // __launch_bounds__ min-blocks variants (register caps)
 };

@@ -1556,31 +1556,16 @@ TOB_DEV double knot_al_cost_at(const DevProblem& P, int k, const double* lamk, c
         // large constraint sets (car_escape: 177 rows per knot; multipliers in global memory): four rows at a time with every
         // load issued before the first use -- the one-row-at-a-time loop paid a dependent load + branch chain of ~340 cycles
         // per row (profiles/r01e3).  Same per-row expressions, same accumulation order.
-        // the multipliers / penalties of the NEXT block are requested before this block is computed: they come from L2
-        // (~270 cycles; the L1 prefetch does not allocate), which one block of arithmetic hides
-        double ln[4], mn[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            ln[q] = (q < rc) ? __ldg(lamk + q) : 0.0;
-            mn[q] = (q < rc) ? __ldg(muk + q) : 0.0;
-        }
         for (; i + 4 <= rc; i += 4) {
             double l4[4], m4[4], c4[4], ra[4], rb_[4], rr[4];
             int eq4[4], kind4[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) { l4[q] = ln[q]; m4[q] = mn[q]; }
-            if (i + 8 <= rc) {
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    ln[q] = __ldg(lamk + i + 4 + q);
-                    mn[q] = __ldg(muk + i + 4 + q);
-                }
-            }
 #pragma unroll
             for (int q = 0; q < 4; q++) {  // every load of the four rows first
                 const DevRow* r = &P.rows[rb + i + q];
                 kind4[q] = r->kind; eq4[q] = r->eq;
                 ra[q] = r->a; rb_[q] = r->b; rr[q] = r->r;
+                l4[q] = __ldg(lamk + i + q);
+                m4[q] = __ldg(muk + i + q);
             }
 #pragma unroll
             for (int q = 0; q < 4; q++) {  // circle rows (the bulk of such sets) without a branch: four independent chains
@@ -2183,6 +2168,7 @@ template <class C> LsJacFn ls_jac_variant(int pc, int minb) {
 template <class C> LsTrialFn ls_trial_variant(int minb, bool all) {
     if constexpr (C::MODEL == 4) {
         if (minb == 4) return all ? ls_trial_kernel<C, 32, 4> : ls_trial_kernel<C, LS_TRIAL_G, 4>;
+        if (minb == 1 && all) return ls_trial_kernel<C, 32, 1>;  // tail mode without a register cap (latency experiment)
     }
     return all ? ls_trial_kernel<C, 32, 3> : ls_trial_kernel<C, LS_TRIAL_G, 3>;
 }
@@ -2223,12 +2209,15 @@ template <class C> int ls_setup_fn(int sm_count, int N, int nrows, LsGrids* g) {
     g->jac_pc = C::PC;
     g->jac_minb = 2;
     g->trial_minb = 3;
+    g->trial_all_minb = 3;
     if constexpr (C::MODEL == 4) {  // quadrotor: kernel variants selectable at run time (tuning)
         g->jac_pc = 1;    // measured (profiles/r01f): one partial direction per thread at <=168 registers (12 warps/SM)
         g->jac_minb = 3;  // beats two directions at 255 registers (8 warps/SM): 4.4 vs 5.4 ms per 16,384 problems
         if (const char* env = getenv("TRAJOPT_B200_JAC_PC")) { const int v = atoi(env); if (v == 1 || v == 2) g->jac_pc = v; }
         if (const char* env = getenv("TRAJOPT_B200_JAC_MINB")) { const int v = atoi(env); if (v >= 2 && v <= 4) g->jac_minb = v; }
         if (const char* env = getenv("TRAJOPT_B200_TRIAL_MINB")) { const int v = atoi(env); if (v == 3 || v == 4) g->trial_minb = v; }
+        g->trial_all_minb = 1;  // tail mode is a latency chain of one warp per problem: no register cap (0.377 -> 0.364 ms, profiles/r01t1)
+        if (const char* env = getenv("TRAJOPT_B200_TRIAL_ALL_MINB")) { const int v = atoi(env); if (v == 1 || v == 3 || v == 4) g->trial_all_minb = v; }
     }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_jac_variant<C>(g->jac_pc, g->jac_minb), 128, 0);
     g->jac = sm_count * (nb > 0 ? nb : 1);
@@ -2271,7 +2260,7 @@ template <class C> void ls_launch_fn(int phase, const LsGrids& g, cudaStream_t s
             ls_bp_sqrt_kernel<C><<<g.accept, 64, 0, st>>>(P, c, lc, cur);
             break;
         case LS_PHASE_TRIAL: ls_trial_variant<C>(g.trial_minb, false)<<<g.trial, 128, g.tab_bytes, st>>>(P, B, c, lc, cur, grp); break;
-        case LS_PHASE_TRIAL_ALL: ls_trial_variant<C>(g.trial_minb, true)<<<g.trial, 128, g.tab_bytes, st>>>(P, B, c, lc, cur, 0); break;
+        case LS_PHASE_TRIAL_ALL: ls_trial_variant<C>(g.trial_all_minb, true)<<<g.trial, 128, g.tab_bytes, st>>>(P, B, c, lc, cur, 0); break;
         case LS_PHASE_ACCEPT: ls_accept_kernel<C><<<g.accept, 64, 0, st>>>(P, B, c, lc, cur); break;
         case LS_PHASE_OUTER: ls_outer_kernel<C><<<g.outer, 32, 0, st>>>(P, B, c, lc, cur); break;
         case LS_PHASE_ACCEPT_TAIL: ls_accept_tail_kernel<C><<<g.outer, 32, 0, st>>>(P, B, c, lc, cur); break;
