@@ -105,6 +105,16 @@ class ClockSampler:
 
 T0 = time.time()
 
+# stdout carries exactly ONE line, the JSON record.  Native libraries do not know that (NCCL prints "NCCL version ..." on
+# stdout when the process group initialises), so file descriptor 1 is pointed at stderr for the whole run and the record is
+# written to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(record):
+    os.write(_REAL_STDOUT, (json.dumps(record) + "\n").encode())
+
 
 def log(msg):
     """progress on stderr (stdout carries only the JSON line)"""
@@ -155,7 +165,7 @@ def run_reference(args, rank, world):
            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
                             "sample": "%d problems/step x %d steps, %d std::threads, g++ -O2 -ffp-contract=off -mfma" % (sample, args.steps, cores)},
            "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 def main():
@@ -397,7 +407,7 @@ def main():
                                    "sample": "first %d problems of the same batch, %d std::threads (one problem per thread), %.1f s; "
                                              "oracle = C++ port of the reference algorithm (Julia not installable here)" % (sample, cores, dt),
                                    "iteration_counts_match_gpu": same}
-        print(json.dumps(out))
+        emit(out)
     bs.close()
     if dist is not None:
         dist.destroy_process_group()
