@@ -1,0 +1,40 @@
+"""Solver-option front-end (no GPU): the reference's defaults, and the options that exist in the reference but are not on the device
+path are refused loudly instead of being ignored (ilqr_solver.jl:7-81)."""
+import pytest
+
+import trajopt_b200 as to
+
+
+def test_defaults_follow_the_reference():
+    o = to.iLQRSolverOptions()
+    assert (o.cost_tolerance, o.gradient_norm_tolerance, o.iterations, o.dJ_counter_limit) == (1e-4, 1e-5, 300, 10)
+    assert (o.iterations_linesearch, o.line_search_lower_bound, o.line_search_upper_bound) == (20, 1e-8, 10.0)
+    assert (o.bp_reg_increase_factor, o.bp_reg_max, o.bp_reg_min, o.bp_reg_fp) == (1.6, 1e8, 1e-8, 10.0)
+    a = to.AugmentedLagrangianSolverOptions()
+    assert (a.iterations, a.penalty_initial, a.penalty_scaling, a.constraint_tolerance) == (30, 1.0, 10.0, 1e-3)
+    assert (a.cost_tolerance_intermediate, a.dual_max, a.penalty_max) == (1e-3, 1e8, 1e8)
+    t = to.ALTROSolverOptions()
+    assert (t.R_inf, t.R_minimum_time, t.dt_max, t.dt_min, t.resolve_feasible_problem) == (1.0, 1.0, 1.0, 1e-3, True)
+
+
+def test_unknown_option_is_an_error():
+    with pytest.raises(TypeError, match="unknown option"):
+        to.iLQRSolverOptions(not_an_option=1)
+
+
+def test_reference_options_outside_the_device_path_are_refused():
+    to.iLQRSolverOptions(bp_reg_type=":control", gradient_type=":todorov").to_c()   # the defaults, in Julia symbol spelling
+    to.iLQRSolverOptions(bp_reg_initial=1.0, bp_sqrt_inv_type=":pseudo").to_c()     # declared but read nowhere in the reference
+    for kw in (dict(bp_reg_type=":state"), dict(gradient_type=":feedforward"), dict(gradient_type="l2")):
+        with pytest.raises(NotImplementedError, match="not on the device path"):
+            to.iLQRSolverOptions(**kw).to_c()
+    with pytest.raises(NotImplementedError, match="projected Newton"):
+        to.ALTROSolverOptions(projected_newton=True).to_c()
+
+
+def test_options_nest_like_the_reference():
+    il = to.iLQRSolverOptions(iterations=50, square_root=True)
+    al = to.AugmentedLagrangianSolverOptions(opts_uncon=il, iterations=7)
+    c = to.ALTROSolverOptions(opts_al=al, R_inf=0.5).to_c()
+    assert c.opts_al.opts_uncon.iterations == 50 and c.opts_al.opts_uncon.square_root == 1
+    assert c.opts_al.iterations == 7 and c.R_inf == 0.5
