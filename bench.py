@@ -168,12 +168,110 @@ def run_reference(args, rank, world):
     emit(out)
 
 
+def kernel_source_hash():
+    """hash of the kernel sources: the ncu traffic figure in profiles/ is only used when it was captured from these sources"""
+    import hashlib
+    h = hashlib.sha1()
+    pkg = os.path.join(ROOT, "trajectoryoptimization.jl-c79d492b-0548-5874-b488-5a62c1d9d0ca_b200", "csrc")
+    for f in ("lockstep.cuh", "engine.cuh", "models.cuh"):
+        h.update(open(os.path.join(pkg, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+class Arm:
+    """one resident batch on this rank: pinned host buffers, the solver handle, device-resident and end-to-end steps"""
+
+    def __init__(self, lib, torch, dist, api, prob, opts, x0_np, local_rank, world, B_global):
+        self.lib, self.torch, self.dist = lib, torch, dist
+        n, m, N = QUAD["n"], QUAD["m"], QUAD["N"]
+        B = len(x0_np)
+        self.B, self.world = B, world
+        self.x0_h = torch.empty((B, n), dtype=torch.float64).pin_memory()
+        self.U0_h = torch.empty((B, N - 1, m), dtype=torch.float64).pin_memory()
+        self.x0_h.numpy()[:] = x0_np
+        self.U0_h.numpy()[:] = prob.U[None]
+        self.X_h = torch.empty((B, N, n), dtype=torch.float64).pin_memory()
+        self.U_h = torch.empty((B, N - 1, m), dtype=torch.float64).pin_memory()
+        self.dts_h = torch.empty((B, N - 1), dtype=torch.float64).pin_memory()
+        self.res_h = torch.empty((B, 32), dtype=torch.uint8).pin_memory()
+        self.bs = api.BatchSolver(prob, B, local_rank, 0, 0)
+        _, self.copts = api.as_altro_options(opts)
+        sp = C.c_void_p()
+        lib.to_stream(self.bs.h, C.byref(sp))
+        self.ext = torch.cuda.ExternalStream(sp.value, device=torch.device("cuda", local_rank))
+        # allgather of the 32-byte result records: every rank contributes `per` records (ragged shards padded)
+        self.per = (B_global + world - 1) // world if B_global else B
+        self.gather_src = torch.zeros((self.per, 32), dtype=torch.uint8, device="cuda")
+        self.gather_dst = torch.empty((world * self.per, 32), dtype=torch.uint8, device="cuda") if world > 1 else None
+        self.check(lib.to_set_batch(self.bs.h, self.x0_h.data_ptr(), self.U0_h.data_ptr(), None))
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError((self.lib.to_last_error(self.bs.h) or b"").decode())
+
+    def resident_step(self):
+        """inputs already in HBM; returns device ms (kernel events + allgather events)"""
+        self.check(self.lib.to_solve_altro(self.bs.h, C.byref(self.copts)))
+        ms = self.bs.kernel_ms()
+        if self.dist is not None:
+            torch = self.torch
+            self.check(self.lib.to_copy_results_device(self.bs.h, self.gather_src.data_ptr()))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.dist.all_gather_into_tensor(self.gather_dst, self.gather_src)
+            e1.record()
+            e1.synchronize()
+            ms += e0.elapsed_time(e1)
+        return ms
+
+    def verify_gather(self, rank):
+        """content check of the NCCL allgather: this rank's slice of the gathered buffer is its own result records, and
+        every rank holds the same gathered buffer (checksum all-reduced with MIN and MAX)"""
+        if self.dist is None:
+            return True
+        torch = self.torch
+        mine = self.gather_dst[rank * self.per:(rank + 1) * self.per]
+        ok = bool(torch.equal(mine, self.gather_src))
+        chk = self.gather_dst.to(torch.int64).sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        self.dist.all_reduce(lo, op=self.dist.ReduceOp.MIN)
+        self.dist.all_reduce(hi, op=self.dist.ReduceOp.MAX)
+        ok = ok and int(lo) == int(hi)
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+        return bool(int(flag))
+
+    def e2e_step(self):
+        """host buffers in, host buffers out, everything on the engine's stream between two events"""
+        torch, lib, bs = self.torch, self.lib, self.bs
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.ext)
+        self.check(lib.to_set_batch(bs.h, self.x0_h.data_ptr(), self.U0_h.data_ptr(), None))
+        self.check(lib.to_solve_altro_async(bs.h, C.byref(self.copts)))
+        self.check(lib.to_get_solution(bs.h, self.X_h.data_ptr(), self.U_h.data_ptr(), self.dts_h.data_ptr()))
+        self.check(lib.to_get_results(bs.h, self.res_h.data_ptr()))
+        e1.record(self.ext)
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    def bytes_moved(self):
+        h2d = self.x0_h.numel() * 8 + self.U0_h.numel() * 8
+        d2h = self.X_h.numel() * 8 + self.U_h.numel() * 8 + self.dts_h.numel() * 8 + self.res_h.numel()
+        return h2d, d2h
+
+    def close(self):
+        self.bs.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=65536, help="problems per GPU per step")
+    ap.add_argument("--batch", type=int, default=65536, help="GLOBAL batch (strong scaling: split over the GPUs); with --scaling weak: per GPU")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--interleave", action="store_true", help="strong scaling: rank r takes problems r, r+N, ... instead of a contiguous slice")
+    ap.add_argument("--no-weak-extra", action="store_true", help="N>1, strong: skip the extra weak-scaling measurement (full batch per GPU)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -189,7 +287,7 @@ def main():
 
     import torch
     import trajopt_b200 as to
-    from trajopt_b200 import abi, api, problems
+    from trajopt_b200 import abi, api, problems, sharding
     lib = abi.load_library()  # raises if the CUDA extension is missing: no fallback
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (the engine has no CPU path)")
@@ -201,119 +299,117 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
 
     prob, opts = make_problem()
-    B = args.batch
-    n, m, N = QUAD["n"], QUAD["m"], QUAD["N"]
-    # synthetic inputs (seeded per rank), in PINNED host memory for the e2e leg
-    x0_np = problems.batch_x0("quadrotor", B, offset=rank * B)
-    x0_h = torch.empty((B, n), dtype=torch.float64).pin_memory()
-    U0_h = torch.empty((B, N - 1, m), dtype=torch.float64).pin_memory()
-    x0_h.numpy()[:] = x0_np
-    U0_h.numpy()[:] = prob.U[None]
-    X_h = torch.empty((B, N, n), dtype=torch.float64).pin_memory()
-    U_h = torch.empty((B, N - 1, m), dtype=torch.float64).pin_memory()
-    dts_h = torch.empty((B, N - 1), dtype=torch.float64).pin_memory()
-    res_h = torch.empty((B, 32), dtype=torch.uint8).pin_memory()
-
-    bs = api.BatchSolver(prob, B, local_rank, 0, 0)
-    mode, copts = api.as_altro_options(opts)
-    stream_ptr = C.c_void_p()
-    lib.to_stream(bs.h, C.byref(stream_ptr))
-    ext = torch.cuda.ExternalStream(stream_ptr.value, device=torch.device("cuda", local_rank))
-    gather_src = torch.empty((B, 32), dtype=torch.uint8, device="cuda")
-    gather_dst = torch.empty((world * B, 32), dtype=torch.uint8, device="cuda") if world > 1 else None
-
-    def check(rc):
-        if rc != 0:
-            raise RuntimeError((lib.to_last_error(bs.h) or b"").decode())
+    strong = args.scaling == "strong"
+    B_global = args.batch if strong else args.batch * world
+    # synthetic inputs: problem b of the GLOBAL batch is seeded by b, whatever the number of GPUs
+    if strong:
+        idx = sharding.shard_indices(B_global, rank, world, args.interleave)
+    else:
+        idx = np.arange(rank * args.batch, (rank + 1) * args.batch)
+    if len(idx) and idx[-1] - idx[0] + 1 == len(idx):
+        x0_np = problems.batch_x0("quadrotor", len(idx), offset=int(idx[0]))
+    else:
+        x0_np = problems.batch_x0("quadrotor", B_global)[idx]
+    B = len(idx)
+    arm = Arm(lib, torch, dist, api, prob, opts, x0_np, local_rank, world, B_global if strong else 0)
+    bs = arm.bs
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def resident_step():
-        """inputs already in HBM; returns device ms (kernel events + allgather events)"""
-        check(lib.to_solve_altro(bs.h, C.byref(copts)))
-        ms = bs.kernel_ms()
-        if dist is not None:
-            check(lib.to_copy_results_device(bs.h, gather_src.data_ptr()))
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            dist.all_gather_into_tensor(gather_dst, gather_src)
-            e1.record()
-            e1.synchronize()
-            ms += e0.elapsed_time(e1)
-        return ms
-
-    def e2e_step():
-        """host buffers in, host buffers out, everything on the engine's stream between two events"""
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(ext)
-        check(lib.to_set_batch(bs.h, x0_h.data_ptr(), U0_h.data_ptr(), None))
-        check(lib.to_solve_altro_async(bs.h, C.byref(copts)))
-        check(lib.to_get_solution(bs.h, X_h.data_ptr(), U_h.data_ptr(), dts_h.data_ptr()))
-        check(lib.to_get_results(bs.h, res_h.data_ptr()))
-        e1.record(ext)
-        e1.synchronize()
-        return e0.elapsed_time(e1)
-
-    log("inputs ready (B=%d per GPU), engine=%s" % (B, os.environ.get("TRAJOPT_B200_ENGINE", "lockstep")))
-    check(lib.to_set_batch(bs.h, x0_h.data_ptr(), U0_h.data_ptr(), None))
+    lockstep = os.environ.get("TRAJOPT_B200_ENGINE", "lockstep")[0] not in "p0"
+    log("inputs ready (B=%d on this GPU, %d global, %s scaling), engine=%s" % (B, B_global, args.scaling, "lockstep" if lockstep else "persistent"))
     for i in range(args.warmup):
-        ms = resident_step()
+        ms = arm.resident_step()
         log("warmup %d: %.1f ms, %d launches" % (i, ms, bs.launches()))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    lockstep = os.environ.get("TRAJOPT_B200_ENGINE", "lockstep")[0] not in "p0"
-    if lockstep:
-        lib.to_debug_phase_timing(bs.h, 1)  # one CUDA event per phase kernel on the engine's stream
-    phase_ms = np.zeros(5)
-    ticks_total = 0
     barrier()
     t_wall0 = time.perf_counter()
     step_ms, kernel_ms = [], []
-    for _ in range(args.steps):
-        ms = resident_step()
+    launches = 0
+    for _ in range(args.steps):       # the timed region: no per-phase events on the stream
+        ms = arm.resident_step()
         step_ms.append(ms)
         kernel_ms.append(bs.kernel_ms())
-        if lockstep:
-            pm = (C.c_double * 5)()
-            lib.to_debug_phase_ms(bs.h, pm)
-            phase_ms += np.array(list(pm))
-            tk = C.c_int32()
-            lib.to_debug_ticks(bs.h, C.byref(tk))
-            ticks_total += tk.value
+        launches += bs.launches()
         log("timed step: %.1f ms" % ms)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = bs.launches() * args.steps
+    gather_ok = arm.verify_gather(rank)
     res = bs.results()
     trials = C.c_int64()
-    check(lib.to_last_linesearch_trials(bs.h, C.byref(trials)))
-    e2e_ms = [e2e_step() for _ in range(max(1, min(2, args.steps)))]
+    arm.check(lib.to_last_linesearch_trials(bs.h, C.byref(trials)))
+    e2e_ms = [arm.e2e_step() for _ in range(max(1, min(2, args.steps)))]
     log("e2e steps: %s ms" % e2e_ms)
     clocks = sampler.stop() if rank == 0 else None
+    # one EXTRA step with a CUDA event per phase kernel (roofline of the dominant kernel); not part of the timed region
+    phase_ms = np.zeros(5)
+    ticks_total, resident_ms, resident_problems, lockstep_passes, phase_step_ms = 0, 0.0, 0, 0, 0.0
+    if lockstep and rank == 0:
+        lib.to_debug_phase_timing(bs.h, 1)
+        arm.check(lib.to_solve_altro(bs.h, C.byref(arm.copts)))
+        phase_step_ms = bs.kernel_ms()
+        pm = (C.c_double * 5)()
+        lib.to_debug_phase_ms(bs.h, pm)
+        phase_ms = np.array(list(pm))
+        tk = C.c_int32()
+        lib.to_debug_ticks(bs.h, C.byref(tk))
+        ticks_total = tk.value
+        rms, rpb, lsp = C.c_double(), C.c_int32(), C.c_int64()
+        lib.to_debug_resident(bs.h, C.byref(rms), C.byref(rpb), C.byref(lsp))
+        resident_ms, resident_problems, lockstep_passes = rms.value, rpb.value, lsp.value
+        lib.to_debug_phase_timing(bs.h, 0)
+        log("phase step: %.1f ms; phases %s; resident kernel %.1f ms (<= %d problems); lockstep passes %d" %
+            (phase_step_ms, np.round(phase_ms, 1), resident_ms, resident_problems, lockstep_passes))
     barrier()
 
     total_ms = float(sum(step_ms))
     e2e_mean = float(np.mean(e2e_ms))
+    rank_ms = [total_ms / args.steps]
     if dist is not None:
+        mine = torch.tensor([total_ms / args.steps], dtype=torch.float64, device="cuda")
+        allms = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allms, mine)
+        rank_ms = [float(x) for x in allms]
         t = torch.tensor([total_ms, e2e_mean], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_mean = float(t[0]), float(t[1])
-        cnt = torch.tensor([float(res["steps"].sum()), float(trials.value)], dtype=torch.float64, device="cuda")
+        cnt = torch.tensor([float(res["steps"].sum()), float(trials.value), float(launches), float(B)], dtype=torch.float64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        steps_all, trials_all = float(cnt[0]), float(cnt[1])
+        steps_all, trials_all, launches_all, B_all = float(cnt[0]), float(cnt[1]), float(cnt[2]), int(cnt[3])
     else:
-        steps_all, trials_all = float(res["steps"].sum()), float(trials.value)
+        steps_all, trials_all, launches_all, B_all = float(res["steps"].sum()), float(trials.value), float(launches), B
+
+    # ---- optional extra: the weak-scaling figure (full batch on every GPU), N > 1 strong runs only ----
+    weak = None
+    if strong and world > 1 and not args.no_weak_extra:
+        h2d_s, d2h_s = arm.bytes_moved()
+        arm.close()
+        x0_w = problems.batch_x0("quadrotor", args.batch, offset=rank * args.batch)
+        arm_w = Arm(lib, torch, dist, api, prob, opts, x0_w, local_rank, world, 0)
+        arm_w.resident_step()
+        barrier()
+        wms = arm_w.resident_step()
+        barrier()
+        tw = torch.tensor([wms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        weak = {"value": world * args.batch / (float(tw[0]) * 1e-3), "unit": "solves/s", "ms_per_step": float(tw[0]),
+                "batch_per_gpu": args.batch, "steps": 1, "warmup": 1, "note": "every rank solves its own full batch (round-1 headline definition)"}
+        arm_w.close()
+        arm = None
+    else:
+        h2d_s, d2h_s = arm.bytes_moved()
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
-        value = world * B / (ms_per_step * 1e-3)
+        value = B_all / (ms_per_step * 1e-3)
         iters_per_s = steps_all / (ms_per_step * 1e-3)
         # ---- roofline ------------------------------------------------------------------------------------
-        iters_rank = float(res["steps"].sum())          # iLQR iterations (= backward passes) of this rank, last step
+        iters_rank = float(res["steps"].sum())          # iLQR iterations (= backward passes) of this rank, one step
         L = float(trials.value) / max(1.0, iters_rank)  # sequential-equivalent line-search trials per iteration
         f_it, b_it = algorithmic_per_iter(L)
         kms = float(np.mean(kernel_ms))
@@ -326,36 +422,43 @@ def main():
         hbm_src = "measured copy bandwidth (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         fp64 = C.c_double()
         lib.to_measure_fp64_peak(local_rank, C.byref(fp64))
-        prof = {}
+        # DRAM traffic of the dominant kernel: only from an ncu capture of THESE kernel sources
+        traffic_pp, traffic_note = None, "no ncu capture in profiles/"
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
+            prof = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+            if prof.get("kernel_source_hash") == kernel_source_hash():
+                traffic_pp, traffic_note = prof.get("ls_bp_kernel_dram_bytes_per_problem_pass"), prof.get("source", "")
+            else:
+                traffic_note = "profiles/dram_traffic.json was captured from other kernel sources (hash %s != %s): not used" % (
+                    prof.get("kernel_source_hash"), kernel_source_hash())
         except Exception:
             pass
-        h2d = x0_h.numel() * 8 + U0_h.numel() * 8
-        d2h = X_h.numel() * 8 + U_h.numel() * 8 + dts_h.numel() * 8 + res_h.numel()
         whole = {"achieved_tflops": iters_rank * f_it / (kms * 1e-3) / 1e12, "achieved_gbs": iters_rank * b_it / (kms * 1e-3) / 1e9,
                  "algorithmic_flops_per_iter": f_it, "algorithmic_bytes_per_iter": b_it, "solve_ms": kms}
         if lockstep and ticks_total > 0 and phase_ms[1] > 0:
-            # dominant kernel: the backward pass (one launch per tick, one pass per live problem per launch)
+            # dominant kernel: the backward pass of the lockstep ticks (one launch per tick, one pass per live problem per launch);
+            # the iterations the resident kernel served are not in this phase time and not in `passes`
             F_bp, B_bp = algorithmic_bp()
-            launches_bp = ticks_total                       # over the timed steps
-            passes = iters_rank * args.steps                # every step solves the same batch: same iteration counts
+            launches_bp = ticks_total
+            passes = float(lockstep_passes) if lockstep_passes > 0 else iters_rank
             bp_ms = float(phase_ms[1])
             ach_tf = passes * F_bp / (bp_ms * 1e-3) / 1e12
             ach_gbs = passes * B_bp / (bp_ms * 1e-3) / 1e9
-            traffic_pp = prof.get("ls_bp_kernel_dram_bytes_per_problem_pass")
             roofline = {
                 "bound": "fp64", "achieved": ach_tf, "peak": fp64.value, "unit": "TFLOP/s", "frac": ach_tf / fp64.value if fp64.value > 0 else None,
-                "traffic": (traffic_pp * passes / launches_bp) if traffic_pp else None,
-                "kernel": "backward-pass phase: tob::ls_bp_kernel<Cfg<4,0,false,false,2>,4,3> (16 lanes per problem; ticks with > 4,096 live "
-                          "problems) and tob::ls_expand_kernel + tob::ls_bp_cta_kernel<..,256,2> (CTA per problem; the other ticks); "
-                          "%.0f%% of the device time of a step" % (100.0 * bp_ms / max(1e-9, float(phase_ms.sum()))),
+                "traffic": (traffic_pp * passes / launches_bp) if traffic_pp else None, "traffic_note": traffic_note,
+                "kernel": "backward-pass phase of the lockstep ticks: tob::ls_bp_kernel<Cfg<4,0,false,false,2>,4,3> (16 lanes per problem; ticks with "
+                          "> 4,096 live problems) and tob::ls_expand_kernel + tob::ls_bp_cta_kernel<..,256,2> (CTA per problem; the other ticks); "
+                          "%.0f%% of the device time of a step" % (100.0 * bp_ms / max(1e-9, phase_step_ms)),
                 "peak_source": "measured register-resident DFMA probe (to_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; "
                                "tensor cores do not apply (13x13 FP64 contractions)",
-                "launches": int(launches_bp), "avg_launch_ms": bp_ms / launches_bp,
+                "launches": int(launches_bp), "avg_launch_ms": bp_ms / launches_bp, "passes": passes,
                 "algorithmic_flops_per_launch": passes * F_bp / launches_bp, "algorithmic_bytes_per_launch": passes * B_bp / launches_bp,
                 "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": hbm_src},
-                "phase_ms_per_step": {k: float(v) / args.steps for k, v in zip(("jac", "bp", "trial", "accept", "outer"), phase_ms)},
+                "phase_ms_per_step": {k: float(v) for k, v in zip(("jac", "bp", "trial", "accept", "outer"), phase_ms)},
+                "resident_kernel": {"ms": resident_ms, "problems_taken_over": resident_problems, "iterations": iters_rank - passes,
+                                    "kernel": "tob::ls_resident_kernel (one CTA per problem, whole iLQR iterations in-kernel)"},
+                "measured_on": "one extra step with a CUDA event per phase kernel (%.1f ms), outside the timed region" % phase_step_ms,
                 "whole_solve": whole,
             }
         else:
@@ -368,34 +471,42 @@ def main():
         out = {
             "metric": "ALTRO solves/s (batched quadrotor N=101)", "value": value, "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "ilqr_iters_per_s": iters_per_s,
             "config": {"workload": "quadrotor ALTRO (AL phase of benchmark/quadrotor_benchmarks.jl, PN off), n=13 m=4 N=101 rk3, "
                                    "u>=0 + terminal box, per-problem random x0 (SURVEY 8d item 3)",
-                       "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d (batch sharded, no solve-path collective)" % world,
-                       "engine": "lockstep" if lockstep else "persistent",
-                       "mean_iters_per_solve": steps_all / (world * B), "mean_linesearch_trials": L,
-                       "ticks_per_step": ticks_total / max(1, args.steps)},
-            "e2e": {"value": world * B / (e2e_mean * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_mean, "timing": "CUDA events on the engine stream around H2D(pinned)+solve+D2H"},
-            "gpu_launches": int(launches),
+                       "global_batch": B_all, "batch_per_gpu": B,
+                       "parallelism": "dp%d: ONE global batch of %d split over the GPUs (%s shards), no solve-path collective, "
+                                      "one NCCL allgather of the 32-byte result records per step" % (
+                                          world, B_all, "interleaved" if args.interleave else "contiguous") if strong else
+                                      "dp%d: every rank solves its own batch (weak)" % world,
+                       "engine": "lockstep + resident tail" if lockstep else "persistent",
+                       "mean_iters_per_solve": steps_all / max(1, B_all), "mean_linesearch_trials": L,
+                       "ticks_per_step": ticks_total},
+            "e2e": {"value": B_all / (e2e_mean * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": int(h2d_s), "d2h_bytes_per_step": int(d2h_s),
+                    "ms_per_step": e2e_mean, "timing": "CUDA events on the engine stream around H2D(pinned)+solve+D2H, max over ranks; bytes are per rank"},
+            "gpu_launches": int(launches_all),
             "roofline": roofline,
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
+            "rank_ms_per_step": rank_ms,
+            "allgather_verified": gather_ok,
             "status_histogram": {str(int(k)): int(v) for k, v in zip(*np.unique(res["status"], return_counts=True))},
         }
+        if weak is not None:
+            out["weak_scaling"] = weak
         ws = C.c_uint64()
         g, sm = C.c_int32(), C.c_int32()
-        if lib.to_debug_grid(bs.h, 0, C.byref(g), C.byref(sm), C.byref(ws)) == 0:
+        if arm is not None and lib.to_debug_grid(bs.h, 0, C.byref(g), C.byref(sm), C.byref(ws)) == 0:
             nws = B if lockstep else g.value
             out["config"]["l2_policy"] = ("inputs (x0+U0 = %.0f MB per GPU) and the solver workspaces (%d x %.2f MB = %.0f MB) exceed the 126 MB L2; "
-                                          "no flush needed between steps" % ((x0_h.numel() + U0_h.numel()) * 8 / 1e6, nws, ws.value * 8 / 1e6,
-                                                                           nws * ws.value * 8 / 1e6))
+                                          "no flush needed between steps" % (h2d_s / 1e6, nws, ws.value * 8 / 1e6, nws * ws.value * 8 / 1e6))
         if not args.no_cpu_baseline and world == 1:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import oracle_py
             cores = host_cores()
             sample = args.cpu_sample or 48 * cores  # ~10 s of host work on the 16-core GPU box
+            sample = min(sample, B)
             log("cpu baseline: %d problems on %d threads" % (sample, cores))
             t0 = time.perf_counter()
             r = oracle_py.solve(prob, opts, x0=x0_np[:sample], B=sample, inner_cap=0, outer_cap=0, threads=cores)
@@ -408,7 +519,8 @@ def main():
                                              "oracle = C++ port of the reference algorithm (Julia not installable here)" % (sample, cores, dt),
                                    "iteration_counts_match_gpu": same}
         emit(out)
-    bs.close()
+    if arm is not None:
+        arm.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -195,7 +195,10 @@ const char *to_last_error(TOHandle h); /* h may be NULL: error of the last faile
  * infeasible-start transform in to_solve_altro (altro_methods.jl:102) and is the initial state
  * trajectory otherwise. */
 int to_set_batch(TOHandle h, const double *x0, const double *U0, const double *X0);
-/* Same, but the pointers are DEVICE pointers already in problem-major layout (no H2D copy). */
+/* Same, but the pointers are DEVICE pointers already in problem-major layout (no H2D copy).
+ * ORDERING: the device-to-device copies are enqueued on the handle's own (non-blocking) stream, see to_stream();
+ * nothing orders them after work the caller still has in flight on another stream.  Synchronise the producer
+ * (or make the handle's stream wait on an event of it) before calling. */
 int to_set_batch_device(TOHandle h, const double *x0, const double *U0, const double *X0);
 /* MPC re-solve without leaving the device (north_star "MPC initial conditions"; the reference's own tools for it are
  * initial_controls!(prob, U), src/problem.jl:149-150, and solver reset!): the initial controls of the next solve become the
@@ -210,7 +213,10 @@ int to_set_trace(TOHandle h, int32_t inner_capacity, int32_t outer_capacity);
 int to_solve_ilqr(TOHandle h, const TOiLQROptions *o);   /* ilqr_methods.jl:3-45 */
 int to_solve_al(TOHandle h, const TOALOptions *o);       /* augmented_lagrangian_methods.jl:2-36 */
 int to_solve_altro(TOHandle h, const TOALTROOptions *o); /* altro_methods.jl:2-53 (projected Newton off) */
-/* Asynchronous variants: enqueue on the handle's stream; to_sync() waits. */
+/* Variant that does not wait for the END of the device work: the result copies of to_get_* and to_sync() wait.
+ * It is not a pure enqueue: the lockstep engine replays its tick until the device-side list of live problems is
+ * empty, so the host thread polls that (pinned) counter while the device works and returns once the last
+ * kernel of the solve has been enqueued. */
 int to_solve_altro_async(TOHandle h, const TOALTROOptions *o);
 int to_sync(TOHandle h);
 /* device time (ms) of the last solve's kernel(s), measured with CUDA events on the handle's stream */
@@ -227,7 +233,9 @@ int to_get_results(TOHandle h, TOResult *results /* B */);
 int to_results_device_ptr(TOHandle h, void **ptr);
 /* histories: inner [B][inner_capacity], outer [B][outer_capacity]; counts per problem */
 int to_get_trace(TOHandle h, TOIterRecord *inner, int32_t *n_inner, TOOuterRecord *outer, int32_t *n_outer);
-/* final multipliers/penalties/active set of the LAST AL solve, packed per problem as the
+/* Recorded only while a trace is enabled (to_set_trace with a non-zero capacity BEFORE the solve); otherwise
+ * to_num_constraint_rows() reports 0 and to_get_duals() returns TO_ERR_INVALID.
+ * final multipliers/penalties/active set of the LAST AL solve, packed per problem as the
  * concatenation over knots of that knot's rows: lambda/mu: B*P doubles, active: B*P bytes,
  * P = to_num_constraint_rows().  (augmented_lagrangian_solver.jl:96-110) */
 int to_num_constraint_rows(TOHandle h, int32_t *P);

@@ -62,7 +62,19 @@ def _compare(ref, gpu, B, atol_xu=1e-10):
 
 @pytest.mark.parametrize("name", [c for c in CASES if c not in ("escape_altro",)])
 def test_parity_small_batches(to, oracle, name):
-    """every parity case on the default (lockstep) engine, in tail mode (few live problems: all step sizes in one launch)"""
+    """every parity case on the default engine.  Few live problems: after the init kernel the CTA-per-problem resident kernel
+    (resident.cuh) runs every problem to completion (the square-root cases stay on the lockstep tick)"""
+    B = 8
+    prob, opts, x0, X0 = CASES[name](B)
+    ref = oracle.solve(prob, opts, x0=x0, X0=X0, B=B, inner_cap=2048, outer_cap=96)
+    gpu = _solve_gpu(to, prob, opts, x0, X0, B)
+    _compare(ref, gpu, B)
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if c not in ("escape_altro",)])
+def test_parity_lockstep_tail(to, oracle, name, monkeypatch):
+    """the lockstep tick in tail mode (all step sizes in one launch, CTA-per-problem backward pass) with the resident kernel off"""
+    monkeypatch.setenv("TRAJOPT_B200_RESIDENT_THRESHOLD", "0")
     B = 8
     prob, opts, x0, X0 = CASES[name](B)
     ref = oracle.solve(prob, opts, x0=x0, X0=X0, B=B, inner_cap=2048, outer_cap=96)
@@ -77,6 +89,7 @@ def test_parity_grouped_line_search(to, oracle, name, monkeypatch):
     lane-group backward pass (ls_bp_kernel) instead of the CTA-per-problem one that small batches get by default"""
     monkeypatch.setenv("TRAJOPT_B200_TAIL_THRESHOLD", "0")
     monkeypatch.setenv("TRAJOPT_B200_BP_CTA_THRESHOLD", "0")
+    monkeypatch.setenv("TRAJOPT_B200_RESIDENT_THRESHOLD", "0")
     B = 8
     prob, opts, x0, X0 = CASES[name](B)
     ref = oracle.solve(prob, opts, x0=x0, X0=X0, B=B, inner_cap=2048, outer_cap=96)
@@ -88,6 +101,7 @@ def test_parity_grouped_line_search(to, oracle, name, monkeypatch):
 def test_parity_lane_group_backward_pass(to, oracle, name, monkeypatch):
     """every case through ls_bp_kernel (16 lanes per problem, the bulk backward pass) with the tail-mode line search"""
     monkeypatch.setenv("TRAJOPT_B200_BP_CTA_THRESHOLD", "0")
+    monkeypatch.setenv("TRAJOPT_B200_RESIDENT_THRESHOLD", "0")
     B = 8
     prob, opts, x0, X0 = CASES[name](B)
     ref = oracle.solve(prob, opts, x0=x0, X0=X0, B=B, inner_cap=2048, outer_cap=96)
@@ -104,6 +118,7 @@ def test_backward_pass_kernels_agree_bitwise(to, monkeypatch):
     x0 = x0.copy()
     pr, _, xr, _ = CASES["quad_regdiv"](8)
     x0[:8] = xr
+    monkeypatch.setenv("TRAJOPT_B200_RESIDENT_THRESHOLD", "0")
     monkeypatch.setenv("TRAJOPT_B200_BP_CTA_THRESHOLD", "0")
     monkeypatch.setenv("TRAJOPT_B200_BP_DEFER_RESTARTS", "0")   # lane-group kernel serves every restart itself
     a = _solve_gpu(to, prob, opts, x0, None, B, inner_cap=0, outer_cap=0)

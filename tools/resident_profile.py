@@ -1,0 +1,34 @@
+"""Cycle profile of the CTA-per-problem resident kernel (resident.cuh): cycles per phase of the iLQR iteration, accumulated by
+CTA 0 over every iteration of the problems it serves.  Usage on the GPU box: python tools/resident_profile.py [case] [B]"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import trajopt_b200 as to  # noqa: E402
+from trajopt_b200 import api  # noqa: E402
+from cases import CASES  # noqa: E402
+
+case = sys.argv[1] if len(sys.argv) > 1 else "quad_altro"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+prob, opts, x0, X0 = CASES[case](B)
+bs = api.BatchSolver(prob, B, 0, 0, 0)
+lib = bs.lib
+bs.set_batch(x0, np.broadcast_to(prob.U, (B,) + prob.U.shape), X0)
+assert lib.to_debug_enable(bs.h, 64) == 0
+bs.solve(opts)
+buf = np.zeros(64, dtype=np.int64)
+assert lib.to_debug_read(bs.h, buf.ctypes.data, 64) == 0
+names = ["jacobians", "expansion", "riccati", "T1 state chains", "T2 costs", "T3+accept 1", "copy", "accept 2 (+outer)"]
+prof = buf[16:32]
+iters = max(1, int(prof[15]))
+tot = prof[:8].sum()
+print("case %s B=%d: kernel %.2f ms; CTA 0 ran %d iLQR iterations, %.1f us per iteration at 1.965 GHz" %
+      (case, B, bs.kernel_ms(), iters, tot / iters / 1965.0))
+for nme, v in zip(names, prof[:8]):
+    print("  %-20s %14d cycles  %5.1f%%  %9.0f cycles/iteration  %7.1f us" % (nme, v, 100.0 * v / max(1, tot), v / iters, v / iters / 1965.0))
+bs.close()

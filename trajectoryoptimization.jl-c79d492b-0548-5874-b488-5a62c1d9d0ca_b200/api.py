@@ -427,6 +427,22 @@ class Marshalled:
         self.desc = d
 
 
+    def mismatch(self, other):
+        """None if `other` (a Marshalled problem) describes the same device problem -- model, horizon, time step, cost blocks and
+        per-knot constraint rows -- else the name of the first field that differs.  A batch shares ONE descriptor: only x0, U0 and
+        X0 are per-problem data (include/trajopt_b200.h: to_create / to_set_batch)."""
+        a, b = self.desc, other.desc
+        for f in ("model", "integrator", "n", "m", "N", "dt", "tf", "c", "cf", "n_classes"):
+            if getattr(a, f) != getattr(b, f):
+                return f
+        for f in ("Q", "R", "H", "q", "r", "Qf", "qf", "class_of_knot", "class_row_start"):
+            if not np.array_equal(getattr(self, f), getattr(other, f)):
+                return f
+        if bytes(self.rows) != bytes(other.rows):
+            return "constraint rows"
+        return None
+
+
 class SolverStats:
     """What `solver.stats` holds in the reference (ilqr_solver.jl:146-154,
     augmented_lagrangian_solver.jl:173-181), rebuilt from the returned histories."""
@@ -545,6 +561,8 @@ class BatchSolver:
         self._check(self.lib.to_num_constraint_rows(self.h, C.byref(P)))
         P = P.value
         lam, mu, act = np.zeros((self.B, P)), np.zeros((self.B, P)), np.zeros((self.B, P), dtype=np.uint8)
+        if P == 0:  # unconstrained solve, or no trace enabled: nothing was recorded (to_get_duals would say so)
+            return lam, mu, act
         self._check(self.lib.to_get_duals(self.h, lam.ctypes.data, mu.ctypes.data, act.ctypes.data))
         return lam, mu, act
 
@@ -567,9 +585,18 @@ def solve_b(prob, opts, device=0, trace=True):
         ic = min(4096, il.iterations * max(1, oc // 2 if oc else 1))
     bs = BatchSolver(p0, B, device, ic, oc)
     try:
+        # the batch shares ONE problem description (cost, constraints, model, horizon); only x0 / U0 / X0 are per-problem data.
+        # A list whose problems differ in anything else must not be solved as copies of problem 0.
+        use_X0 = not np.all(np.isnan(p0.X[0]))
+        for b, p in enumerate(probs[1:], 1):
+            diff = bs.marsh.mismatch(Marshalled(p))
+            if diff is None and (not np.all(np.isnan(p.X[0]))) != use_X0:
+                diff = "X (infeasible start given for some problems only)"
+            if diff is not None:
+                raise ValueError("batched solve!: problem %d differs from problem 0 in `%s`; a batch shares one problem description "
+                                 "(only x0, U and X may differ) -- solve such problems in separate batches" % (b, diff))
         x0 = np.stack([p.x0 for p in probs])
         U0 = np.stack([p.U for p in probs])
-        use_X0 = not np.all(np.isnan(p0.X[0]))
         X0 = np.stack([p.X for p in probs]) if use_X0 else None
         bs.set_batch(x0, U0, X0)
         bs.solve(opts)

@@ -72,41 +72,56 @@ def generate():
     return files
 
 
-def _deps_hash():
+KERNEL_DEPS = ("engine.cuh", "lockstep.cuh", "resident.cuh", "sqrt_bp.cuh", "engine_host.h", "models.cuh", "../build.py", "../../include/trajopt_b200.h")
+HOST_DEPS = ("engine_host.h", "../build.py", "../../include/trajopt_b200.h")
+
+
+def _hash(src):
+    """hash of one translation unit and the headers it includes (instances: every kernel header; capi/peak/registry: host headers)"""
     h = hashlib.sha1()
-    for f in ("engine.cuh", "lockstep.cuh", "sqrt_bp.cuh", "engine_host.h", "models.cuh", "capi.cu", "peak.cu", "../build.py", "../../include/trajopt_b200.h"):
-        h.update(open(os.path.join(CSRC, f), "rb").read())
+    deps = KERNEL_DEPS if os.path.basename(src).startswith("inst_") else HOST_DEPS
+    for f in (src,) + tuple(os.path.join(CSRC, d) for d in deps):
+        h.update(open(f, "rb").read())
+    h.update(" ".join(ARCH + FLAGS).encode())
     return h.hexdigest()
 
 
 def _compile(src):
     obj = os.path.join(GEN, os.path.basename(src).replace(".cu", ".o"))
+    stamp, hsh = obj + ".stamp", _hash(src)
+    log = obj + ".log"
+    if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == hsh:
+        return src, obj, 0, open(log).read() if os.path.exists(log) else "", False
     cmd = [NVCC] + ARCH + FLAGS + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
-    return src, obj, r.returncode, r.stdout + r.stderr
+    if r.returncode == 0:
+        open(stamp, "w").write(hsh)
+        open(log, "w").write(r.stdout + r.stderr)
+    return src, obj, r.returncode, r.stdout + r.stderr, True
 
 
 def build(force=False, verbose=False, jobs=None):
     files = generate()
-    stamp = os.path.join(GEN, "stamp")
-    hsh = _deps_hash()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == hsh:
-        return LIB
+    if force:
+        for f in os.listdir(GEN):
+            if f.endswith(".stamp"):
+                os.remove(os.path.join(GEN, f))
     jobs = jobs or max(1, (os.cpu_count() or 4))
-    objs, logs = [], []
+    objs, logs, rebuilt = [], [], False
     with cf.ThreadPoolExecutor(jobs) as ex:
-        for src, obj, rc, out in ex.map(_compile, files):
+        for src, obj, rc, out, did in ex.map(_compile, files):
             logs.append("== %s\n%s" % (os.path.basename(src), out))
             if rc != 0:
                 sys.stderr.write(out)
                 raise RuntimeError("nvcc failed on %s" % src)
             objs.append(obj)
+            rebuilt = rebuilt or did
     open(os.path.join(GEN, "ptxas.log"), "w").write("\n".join(logs))
     if verbose:
         print("\n".join(logs))
-    cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
-    subprocess.check_call(cmd)
-    open(stamp, "w").write(hsh)
+    if rebuilt or not os.path.exists(LIB):
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        subprocess.check_call(cmd)
     return LIB
 
 

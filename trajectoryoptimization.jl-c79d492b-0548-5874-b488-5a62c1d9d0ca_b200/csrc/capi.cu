@@ -51,6 +51,8 @@ struct Variant {
     double* cand_alloc = nullptr;  // tail-mode candidate trajectories (lockstep): 32 per list slot
     unsigned int cand_slots = 0;
     double* cand_bulk = nullptr;   // bulk candidate trajectories: trial_group per problem
+    double* res_scratch = nullptr; // resident kernel: cost scratch of res_slots CTAs
+    unsigned int res_slots = 0;
 };
 
 }  // namespace
@@ -87,6 +89,10 @@ struct TOSolver {
     int ticks = 0;               // lockstep ticks enqueued by the last solve
     int phase_timing = 0;        // 1: time every phase kernel of the lockstep engine with CUDA events
     double phase_ms[5] = {0, 0, 0, 0, 0};  // device ms of the last solve: jac, bp, trial, accept, outer
+    double resident_ms = 0;      // device ms of the resident kernel of the last solve (phase timing / tick log only)
+    int resident_problems = 0;   // upper bound of the problems the resident kernel of the last solve took over
+    long long lockstep_passes = 0;  // iLQR iterations of the last solve that ran in lockstep ticks (the rest ran in the resident kernel)
+    cudaEvent_t ev_res0 = nullptr, ev_res1 = nullptr;
     unsigned int* h_counts = nullptr;  // pinned ring of active-list sizes read back from the device
     cudaEvent_t ring_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
@@ -139,6 +145,9 @@ void free_variant(Variant& v) {
     if (v.lc.counts) cudaFree(v.lc.counts);
     if (v.cand_alloc) cudaFree(v.cand_alloc);
     if (v.cand_bulk) cudaFree(v.cand_bulk);
+    if (v.res_scratch) cudaFree(v.res_scratch);
+    v.res_scratch = nullptr;
+    v.res_slots = 0;
     v.cand_bulk = nullptr;
     v.cand_alloc = nullptr;
     v.cand_slots = 0;
@@ -334,6 +343,15 @@ int ensure_engine_buffers(TOSolver* s, Variant& v) {
             v.cand_bulk = nullptr;
         }
     }
+    // resident kernel (one CTA per problem, runs to completion): as many slots as CTAs can be resident, at most the candidate slots
+    {
+        unsigned int slots = std::min<unsigned int>((unsigned int)std::max(0, v.grids.res_capacity), v.cand_slots);
+        if (const char* env = getenv("TRAJOPT_B200_RESIDENT_THRESHOLD")) slots = std::min<unsigned int>(slots, (unsigned int)atoi(env));  // 0 disables
+        const size_t per = 2 * (size_t)N * 32;  // res_scratch_doubles(N)
+        if (slots > 0 && cudaMalloc(&v.res_scratch, (size_t)slots * per * sizeof(double)) == cudaSuccess) v.res_slots = slots;
+        else { cudaGetLastError(); v.res_scratch = nullptr; v.res_slots = 0; }
+        v.lc.res_scratch = v.res_scratch;
+    }
     v.ls_ready = true;
     return 0;
 }
@@ -341,7 +359,17 @@ int ensure_engine_buffers(TOSolver* s, Variant& v) {
 // the lockstep engine: init kernel, then replay the tick (jac, bp, trial groups, accept, outer)
 // until the active list is empty.  The host learns the list size from an asynchronous read-back
 // that trails the enqueued work by LAG ticks, so the stream never drains between ticks.
+int run_lockstep_impl(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c);
 int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
+    const int rc = run_lockstep_impl(s, v, Bt, c);
+    if (rc == 0 && s->phase_timing) {  // diagnostics only: costs a stream synchronisation
+        unsigned long long passes = 0;
+        if (cudaStreamSynchronize(s->stream) == cudaSuccess && cudaMemcpy(&passes, v.lc.counts + 8, 8, cudaMemcpyDeviceToHost) == cudaSuccess)
+            s->lockstep_passes += (long long)passes;
+    }
+    return rc;
+}
+int run_lockstep_impl(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
     const int LAG = 4, RING = 8;
     cudaStream_t st = s->stream;
     CK_RET(s, cudaMemsetAsync(v.lc.counts, 0, 64, st));
@@ -416,8 +444,36 @@ int run_lockstep(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl& c) {
         cudaEventRecord(e, st);
         tick_ev.push_back(e);
     };
+    const unsigned int res_threshold = (!c.o.opts_uncon.square_root && ntrial <= 32 && v.cand_alloc) ? v.res_slots : 0u;
     for (long long t = 0; t < max_ticks; t++) {
         const int cur = (int)(t & 1);
+        if (known_active <= res_threshold) {
+            // few live problems: each gets a CTA that runs it to completion (resident.cuh) -- the last launch of the solve
+            LsCtl lcr = v.lc;
+            lcr.cand = v.cand_alloc;
+            lcr.cand_width = 32;
+            lcr.cand_by_problem = 0;
+            if (collect) { cudaEventRecord(s->ev_res0, st); }
+            v.ki->ls_launch(LS_PHASE_RESIDENT, v.grids, st, v.P, Bt, c, lcr, cur, (int)known_active);
+            CK_RET(s, cudaGetLastError());
+            if (collect) { cudaEventRecord(s->ev_res1, st); }
+            s->launches += 1;
+            s->resident_problems = (int)known_active;
+            dump_ticks();
+            if (collect) {
+                float ms = 0.f;
+                cudaEventSynchronize(s->ev_res1);
+                cudaEventElapsedTime(&ms, s->ev_res0, s->ev_res1);
+                s->resident_ms = ms;
+                if (tick_log) {
+                    if (FILE* f = fopen(tick_log, "a")) {
+                        fprintf(f, "# resident kernel: %.4f ms, took over <= %u problems after %d ticks\n", ms, known_active, s->ticks);
+                        fclose(f);
+                    }
+                }
+            }
+            return 0;
+        }
         v.ki->ls_launch(LS_PHASE_JAC, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
         mark();
         const bool bp_cta = !c.o.opts_uncon.square_root && known_active <= cta_threshold;
@@ -492,10 +548,15 @@ bool constrained(const TOSolver* s) {
     return false;
 }
 
+// Multipliers / penalties / active set of the final iterate are exported only while a trace is enabled (to_set_trace with a
+// non-zero capacity): they cost 17 bytes per constraint row and problem.  Whenever the buffers do not match the variant that is
+// about to run they are released, so a kernel never sees a buffer sized for another row count.
 int ensure_dual_buffers(TOSolver* s, int P) {
-    if (s->inner_cap <= 0 && s->outer_cap <= 0) { s->dual_P = 0; return 0; }  // only in diagnostic (trace) mode
-    if (P == s->dual_P && s->lam_out) return 0;
-    if (s->lam_out) { cudaFree(s->lam_out); cudaFree(s->mu_out); cudaFree(s->act_out); s->lam_out = s->mu_out = nullptr; s->act_out = nullptr; }
+    if (s->inner_cap <= 0 && s->outer_cap <= 0) P = 0;
+    if (P == s->dual_P && (P == 0 || s->lam_out)) return 0;
+    if (s->lam_out) { cudaFree(s->lam_out); cudaFree(s->mu_out); cudaFree(s->act_out); }
+    s->lam_out = s->mu_out = nullptr;
+    s->act_out = nullptr;
     s->dual_P = P;
     if (P == 0) return 0;
     size_t cnt = (size_t)s->B * P;
@@ -520,7 +581,7 @@ int launch(TOSolver* s, int which, int mode, const TOALOptions& alo, bool altro_
     Bt.outer = s->outer; Bt.n_outer = s->n_outer; Bt.outer_cap = s->outer_cap;
     int rc = ensure_dual_buffers(s, mode == 1 ? v.P.Ptot : 0);
     if (rc) return rc;
-    Bt.lam_out = (mode == 1) ? s->lam_out : nullptr; Bt.mu_out = s->mu_out; Bt.act_out = s->act_out;
+    Bt.lam_out = (mode == 1) ? s->lam_out : nullptr; Bt.mu_out = Bt.lam_out ? s->mu_out : nullptr; Bt.act_out = Bt.lam_out ? s->act_out : nullptr;
     DevCtl c{};
     c.mode = mode; c.altro_init = altro_init; c.projection_first = projection_first; c.accumulate = accumulate;
     c.write_solution = 1;
@@ -566,6 +627,9 @@ int solve_common(TOSolver* s, int api_mode, const TOALTROOptions& ao, bool sync)
     s->launches = 0;
     s->ticks = 0;
     for (double& v : s->phase_ms) v = 0.0;
+    s->resident_ms = 0.0;
+    s->resident_problems = 0;
+    s->lockstep_passes = 0;
     const bool con = constrained(s);
     const double* X0_in = s->has_X0 ? s->X0 : nullptr;
     CK_RET(s, cudaMemsetAsync(s->queue, 0, 256, s->stream));
@@ -674,6 +738,7 @@ int to_create(const TOProblemDesc* desc, int32_t B, int32_t device, TOHandle* ou
     bool ok = true;
     ok &= cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok &= cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess;
+    ok &= cudaEventCreate(&s->ev_res0) == cudaSuccess && cudaEventCreate(&s->ev_res1) == cudaSuccess;
     ok &= cudaMalloc(&s->x0, (size_t)B * n * 8) == cudaSuccess;
     ok &= cudaMalloc(&s->U0, (size_t)B * (N - 1) * m * 8) == cudaSuccess;
     ok &= cudaMalloc(&s->X, (size_t)B * N * n * 8) == cudaSuccess;
@@ -701,6 +766,8 @@ void to_destroy(TOHandle s) {
     for (auto& e : s->ring_ev) if (e) cudaEventDestroy(e);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev_res0) cudaEventDestroy(s->ev_res0);
+    if (s->ev_res1) cudaEventDestroy(s->ev_res1);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -868,7 +935,8 @@ int to_get_duals(TOHandle s, double* lambda, double* mu, uint8_t* active) {
     if (!s) return TO_ERR_INVALID;
     CK_RET(s, cudaSetDevice(s->device));
     CK_RET(s, cudaStreamSynchronize(s->stream));
-    if (s->dual_P == 0 || !s->lam_out) return 0;
+    if (s->dual_P == 0 || !s->lam_out)
+        return s->fail(TO_ERR_INVALID, "to_get_duals: no multipliers were recorded (enable a trace with to_set_trace before an AL / ALTRO solve)");
     size_t cnt = (size_t)s->B * s->dual_P;
     if (lambda) CK_RET(s, cudaMemcpy(lambda, s->lam_out, cnt * 8, cudaMemcpyDeviceToHost));
     if (mu) CK_RET(s, cudaMemcpy(mu, s->mu_out, cnt * 8, cudaMemcpyDeviceToHost));
@@ -950,6 +1018,14 @@ int to_debug_phase_timing(TOHandle s, int32_t enable) {
 int to_debug_phase_ms(TOHandle s, double* ms) {
     if (!s || !ms) return TO_ERR_INVALID;
     for (int i = 0; i < 5; i++) ms[i] = s->phase_ms[i];
+    return 0;
+}
+// resident kernel of the last solve: device ms (needs phase timing or the tick log) and the problems it took over
+int to_debug_resident(TOHandle s, double* ms, int32_t* problems, int64_t* lockstep_passes) {
+    if (!s || !ms || !problems || !lockstep_passes) return TO_ERR_INVALID;
+    *ms = s->resident_ms;
+    *problems = s->resident_problems;
+    *lockstep_passes = s->lockstep_passes;
     return 0;
 }
 int to_debug_ticks(TOHandle s, int32_t* ticks) {

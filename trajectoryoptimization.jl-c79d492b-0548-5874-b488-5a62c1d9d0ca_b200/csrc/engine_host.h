@@ -94,10 +94,11 @@ struct LsCtl {
     double* cand;                  // candidate trajectories of the line search, [slot][X|U][element][cand_width step sizes]; null = off
     int cand_width;                // step sizes per launch group (8 in the bulk, 32 in tail mode)
     int cand_by_problem;           // 1: slot = problem id (bulk buffer), 0: slot = position in the active list (tail buffer)
+    double* res_scratch;           // ls_resident_kernel: per-CTA cost scratch (res_scratch_doubles(N) each)
 };
 
 constexpr int LS_BP_INLINE_RESTARTS = 2;  // regularisation increases a bulk backward-pass launch serves itself before handing the problem over
-enum { LS_PHASE_INIT = 0, LS_PHASE_JAC, LS_PHASE_BP, LS_PHASE_TRIAL, LS_PHASE_ACCEPT, LS_PHASE_OUTER, LS_PHASE_TRIAL_ALL, LS_PHASE_BP_SQRT, LS_PHASE_ACCEPT_TAIL, LS_PHASE_EXPAND, LS_PHASE_BP_CTA };
+enum { LS_PHASE_INIT = 0, LS_PHASE_JAC, LS_PHASE_BP, LS_PHASE_TRIAL, LS_PHASE_ACCEPT, LS_PHASE_OUTER, LS_PHASE_TRIAL_ALL, LS_PHASE_BP_SQRT, LS_PHASE_ACCEPT_TAIL, LS_PHASE_EXPAND, LS_PHASE_BP_CTA, LS_PHASE_RESIDENT };
 struct LsGrids {
     int init, jac, bp, trial, accept, outer;  // grid sizes (persistent, grid-stride)
     int bp_smem, bp_groups_per_block, trial_group;
@@ -105,6 +106,7 @@ struct LsGrids {
     int jac_pc;  // partial directions per thread in the Jacobian kernel
     int jac_minb, trial_minb, bp_minb, trial_all_minb;
     int expand, bp_cta, bp_cta_smem, occ_bp_cta, bp_cta_minb;  // latency path of the backward pass (ls_expand_kernel + ls_bp_cta_kernel)
+    int res_threads, res_smem, res_capacity, res_minb;  // CTA-per-problem resident kernel (resident.cuh): block size, dynamic smem, resident CTAs
     int tab_bytes;  // dynamic shared memory of the per-block copy of the knot tables / constraint rows  // __launch_bounds__ min-blocks variants (register caps)
 };
 

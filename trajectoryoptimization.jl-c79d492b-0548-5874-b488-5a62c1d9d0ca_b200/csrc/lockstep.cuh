@@ -270,22 +270,15 @@ __global__ void __launch_bounds__(32) ls_outer_kernel(const DevProblem P, const 
 template <int MODEL> struct TrivialDirs { static constexpr int value = 0; };
 template <> struct TrivialDirs<4> { static constexpr int value = 3; };
 
-template <class C, int PC, int MINB>
-__global__ void __launch_bounds__(128, MINB) ls_jac_kernel(const DevProblem P, const LsCtl lc, const int cur) {
+// one work item of the Jacobian phase: knot k of the problem with workspace ws, chunk `ch` of PC partial directions
+template <class C, int PC> __host__ __device__ constexpr int ls_jac_chunks() {
+    return (C::PT - ((!C::MT) ? TrivialDirs<C::MODEL>::value : 0) + PC - 1) / PC;
+}
+template <class C, int PC>
+__device__ __forceinline__ void ls_jac_item(const DevProblem& P, double* ws, const WsLayout& L, const int k, const int ch) {
     constexpr int TZ = (!C::MT) ? TrivialDirs<C::MODEL>::value : 0;
-    constexpr int NCH = (C::PT - TZ + PC - 1) / PC;
     typedef Dual<PC> D;
-    const unsigned int na = lc.counts[cur];
-    if (blockIdx.x == 0 && threadIdx.x == 0) { lc.counts[cur ^ 1] = 0; lc.counts[2] = 0; lc.counts[3] = 0; lc.counts[4] = 0; lc.counts[5] = 0; }
-    const int N = P.N;
-    const unsigned int per = (unsigned int)(N - 1) * NCH;
-    const unsigned long long items = (unsigned long long)na * per;
-    const WsLayout L = ws_layout<C>(N, P.Ptot, false);
-    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < items; t += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned int a = (unsigned int)(t / per), it = (unsigned int)(t - (unsigned long long)a * per);
-        const int b = lc.list[cur][a];
-        double* ws = lc.ws + (size_t)b * lc.ws_stride;
-        const int k = it / NCH, ch = it - k * NCH;
+    {
         const double* xk = ws + L.X + (size_t)k * C::n;
         const double* uk = ws + L.U + (size_t)k * C::m;
         double* ab = ws + L.Z + (size_t)k * C::ZA;
@@ -371,6 +364,26 @@ __global__ void __launch_bounds__(128, MINB) ls_jac_kernel(const DevProblem P, c
     }
 }
 
+template <class C, int PC, int MINB>
+__global__ void __launch_bounds__(128, MINB) ls_jac_kernel(const DevProblem P, const LsCtl lc, const int cur) {
+    constexpr int NCH = ls_jac_chunks<C, PC>();
+    const unsigned int na = lc.counts[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        lc.counts[cur ^ 1] = 0; lc.counts[2] = 0; lc.counts[3] = 0; lc.counts[4] = 0; lc.counts[5] = 0;
+        *reinterpret_cast<unsigned long long*>(&lc.counts[8]) += na;  // iLQR iterations served by lockstep ticks (bench roofline)
+    }
+    const int N = P.N;
+    const unsigned int per = (unsigned int)(N - 1) * NCH;
+    const unsigned long long items = (unsigned long long)na * per;
+    const WsLayout L = ws_layout<C>(N, P.Ptot, false);
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < items; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned int a = (unsigned int)(t / per), it = (unsigned int)(t - (unsigned long long)a * per);
+        const int b = lc.list[cur][a];
+        const int k = it / NCH, ch = it - k * NCH;
+        ls_jac_item<C, PC>(P, lc.ws + (size_t)b * lc.ws_stride, L, k, ch);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // backward pass: GS lanes per problem, lane j owns column j
 // ------------------------------------------------------------------------------------------
@@ -420,14 +433,21 @@ __device__ __forceinline__ void prefetch_span(const double* base, int count, int
         asm volatile("prefetch.global.L1 [%0];\n" ::"l"(q));
 }
 
+// shared memory of a lane group that only evaluates expansions (ls_resident_kernel): the minimum-time exchange vectors
 template <class C>
+struct alignas(16) BpExpSmem {
+    static constexpr int XU = (C::n + C::m + 1) & ~1;
+    double xu[XU], vQx[C::nq], vQu[C::mq];
+};
+
+template <class C, class SM = BpSmem<C>>
 struct BpGroup {
     static constexpr int n = C::n, m = C::m, n0 = C::n0, m0 = C::m0, nq = C::nq, mq = C::mq;
     static constexpr int GS = ls_group_size<C>();
     static constexpr int DL = (n < GS) ? n : 0;  // lane that solves for the feed-forward term d
     static constexpr int LDn = BpSmem<C>::LDn, LDm = BpSmem<C>::LDm, LDZ = BpSmem<C>::LDZ, LAMCAP = BpSmem<C>::LAMCAP;
     const DevProblem& P;
-    BpSmem<C>& sm;
+    SM& sm;
     double* ws;
     const WsLayout L;
     const int j;            // lane within the group
@@ -459,7 +479,7 @@ struct BpGroup {
         }
     }
 
-    __device__ BpGroup(const DevProblem& P_, BpSmem<C>& s_, double* ws_, int j_, unsigned gmask_, bool al_on_, const TOiLQROptions& io_)
+    __device__ BpGroup(const DevProblem& P_, SM& s_, double* ws_, int j_, unsigned gmask_, bool al_on_, const TOiLQROptions& io_)
         : P(P_), sm(s_), ws(ws_), L(ws_layout<C>(P_.N, P_.Ptot, false)), j(j_), gmask(gmask_), al_on(al_on_), io(io_) {}
 
     __device__ void gsync() { __syncwarp(gmask); }
@@ -1297,23 +1317,15 @@ struct alignas(16) BpCtaSmem {
     int pd;
 };
 
-template <class C, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) ls_bp_cta_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
+// the backward pass of ONE problem by the whole CTA (NT threads; every thread of the block must call it)
+template <class C, int NT>
+__device__ __forceinline__ void ls_bp_cta_problem(const DevProblem& P, const TOiLQROptions& io, double* ws, const WsLayout& L,
+                                                  BpCtaSmem<C>& sm, LsState* st, const int tid) {
     constexpr int n = C::n, m = C::m, LDZ = C::LDZ;
     constexpr int LDn = BpCtaSmem<C>::LDn, LDm = BpCtaSmem<C>::LDm;
     typedef typename BpGroup<C>::LU LU;
-    extern __shared__ __align__(16) unsigned char ls_smem_raw[];
-    BpCtaSmem<C>& sm = *reinterpret_cast<BpCtaSmem<C>*>(ls_smem_raw);
     const int N = P.N;
-    const WsLayout L = ws_layout<C>(N, P.Ptot, false);
-    const int tid = threadIdx.x;
-    const int* list = (cur & 4) ? lc.restart_list : lc.list[cur & 1];
-    const unsigned int na = (cur & 4) ? lc.counts[5] : lc.counts[cur & 1];
-    const TOiLQROptions io = ctl.o.opts_uncon;
-    for (unsigned int a = blockIdx.x; a < na; a += gridDim.x) {
-        const int b = list[a];
-        LsState* st = &lc.st[b];
-        double* ws = lc.ws + (size_t)b * lc.ws_stride;
+    {
         double rho = st->rho, drho = st->drho;  // uniform over the CTA
         auto reg_update = [&](bool increase) {  // ilqr_methods.jl:164-176
             const double f = io.bp_reg_increase_factor;
@@ -1527,6 +1539,21 @@ __global__ void __launch_bounds__(NT, MINB) ls_bp_cta_kernel(const DevProblem P,
     }
 }
 
+template <class C, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ls_bp_cta_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
+    extern __shared__ __align__(16) unsigned char ls_smem_raw[];
+    BpCtaSmem<C>& sm = *reinterpret_cast<BpCtaSmem<C>*>(ls_smem_raw);
+    const WsLayout L = ws_layout<C>(P.N, P.Ptot, false);
+    const int tid = threadIdx.x;
+    const int* list = (cur & 4) ? lc.restart_list : lc.list[cur & 1];
+    const unsigned int na = (cur & 4) ? lc.counts[5] : lc.counts[cur & 1];
+    const TOiLQROptions io = ctl.o.opts_uncon;
+    for (unsigned int a = blockIdx.x; a < na; a += gridDim.x) {
+        const int b = list[a];
+        ls_bp_cta_problem<C, NT>(P, io, lc.ws + (size_t)b * lc.ws_stride, L, sm, &lc.st[b], tid);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // line search: thread per (problem, step size); G consecutive lanes serve one problem
 // ------------------------------------------------------------------------------------------
@@ -1610,7 +1637,7 @@ struct Rollout {
     // Line-search rollout with the per-knot inputs (x_k, u_k, K_k, d_k, lambda_k, mu_k) staged in shared memory one knot
     // ahead by cp.async: the `nact` lanes that serve one problem (lane index t within them, warp mask amask) share one
     // double buffer `stg`.  Arithmetic identical to run<false, CAND, CW>.
-    template <bool CAND, int CW>
+    template <bool CAND, int CW, bool COST = true>
     static __device__ bool run_staged(const DevProblem& P, const TOiLQROptions& io, double* ws, const WsLayout& L, const double* x0,
                                       double alpha, bool al_on, double& Jt, double* XB, double* UB, int slot, double* stg, int t,
                                       int nact, unsigned amask) {
@@ -1625,7 +1652,7 @@ struct Rollout {
             const double* uk = ws + L.U + (size_t)k * m;
             const double* kd = ws + L.KD + (size_t)k * C::KDS;
             for (int e = t; e < SS; e += nact) cp_async8(dst + e, (e < n) ? (xk + e) : ((e < n + m) ? (uk + (e - n)) : (kd + (e - n - m))));
-            if (al_on) {
+            if (COST && al_on) {
                 const int rc = P.knot_row_count[k], lo = P.knot_lam_off[k];
                 if (rc <= LC) {
                     for (int e = t; e < rc; e += nact) {
@@ -1668,8 +1695,8 @@ struct Rollout {
                 for (int c = 0; c < n; c++) acc = fma(Kk[c * m + i], dx[c], acc);
                 ub[i] = (Uk[i] + acc) + alpha * dk[i];
             }
-            J += stage_cost<C>(P, xb, ub);
-            if (al_on) {
+            if (COST) J += stage_cost<C>(P, xb, ub);
+            if (COST && al_on) {
                 const int rc = P.knot_row_count[k];
                 const bool staged = (rc <= LC);
                 const int lo = P.knot_lam_off[k];
@@ -1709,8 +1736,8 @@ struct Rollout {
             double uz[m];
 #pragma unroll
             for (int i = 0; i < m; i++) uz[i] = 0.0;
-            J += term_cost<C>(P, xb);
-            if (al_on) Jc += knot_al_cost<C>(P, N - 1, lam, mu, xb, uz);
+            if (COST) J += term_cost<C>(P, xb);
+            if (COST && al_on) Jc += knot_al_cost<C>(P, N - 1, lam, mu, xb, uz);
             if (CAND) {
 #pragma unroll
                 for (int i = 0; i < n; i++) XB[cand_index((size_t)(N - 1) * n + i, slot, CW)] = xb[i];
@@ -2143,6 +2170,10 @@ __global__ void __launch_bounds__(64) ls_accept_kernel(const DevProblem P, const
 }
 
 
+}  // namespace tob
+#include "resident.cuh"
+namespace tob {
+
 // ------------------------------------------------------------------------------------------
 // host-side launch table of the lockstep kernels of one configuration
 // ------------------------------------------------------------------------------------------
@@ -2185,6 +2216,16 @@ template <class C> LsBpFn ls_bp_cta_variant(int minb) {
         if (minb == 4) return ls_bp_cta_kernel<C, ls_bp_cta_threads<C>(), 4>;
     }
     return ls_bp_cta_kernel<C, ls_bp_cta_threads<C>(), 2>;
+}
+
+template <class C> constexpr int ls_res_threads() {
+    return ls_bp_cta_threads<C>() > 32 * RollRoles<C>::R ? ls_bp_cta_threads<C>() : 32 * RollRoles<C>::R;
+}
+typedef void (*LsResFn)(const DevProblem, const DevBatch, const DevCtl, const LsCtl, const int);
+template <class C> LsResFn ls_resident_variant(int minb) {
+    constexpr int JPC = (C::MODEL == 4) ? 1 : C::PC;  // partial directions per Jacobian item (values do not depend on the chunking)
+    if (minb == 2) return ls_resident_kernel<C, ls_res_threads<C>(), 2, JPC>;
+    return ls_resident_kernel<C, ls_res_threads<C>(), 1, JPC>;
 }
 
 template <class C> unsigned long long ls_ws_doubles_fn(int N, int Ptot) { return ws_layout<C>(N, Ptot, false).total; }
@@ -2244,6 +2285,18 @@ template <class C> int ls_setup_fn(int sm_count, int N, int nrows, LsGrids* g) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_bp_cta_variant<C>(g->bp_cta_minb), ls_bp_cta_threads<C>(), g->bp_cta_smem);
     g->occ_bp_cta = nb;
     g->bp_cta = sm_count * (nb > 0 ? nb : 1);
+    // CTA-per-problem resident kernel
+    g->res_threads = ls_res_threads<C>();
+    g->res_smem = (int)ResLayout<C, ls_res_threads<C>()>::total(N, nrows);
+    g->res_minb = 2;
+    if (const char* env = getenv("TRAJOPT_B200_RESIDENT_MINB")) { const int v = atoi(env); if (v == 1 || v == 2) g->res_minb = v; }
+    g->res_capacity = 0;
+    if (cudaFuncSetAttribute(ls_resident_variant<C>(g->res_minb), cudaFuncAttributeMaxDynamicSharedMemorySize, g->res_smem) == cudaSuccess) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_resident_variant<C>(g->res_minb), g->res_threads, g->res_smem);
+        g->res_capacity = sm_count * (nb > 0 ? nb : 0);
+    } else {
+        cudaGetLastError();
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
@@ -2264,6 +2317,7 @@ template <class C> void ls_launch_fn(int phase, const LsGrids& g, cudaStream_t s
         case LS_PHASE_ACCEPT: ls_accept_kernel<C><<<g.accept, 64, 0, st>>>(P, B, c, lc, cur); break;
         case LS_PHASE_OUTER: ls_outer_kernel<C><<<g.outer, 32, 0, st>>>(P, B, c, lc, cur); break;
         case LS_PHASE_ACCEPT_TAIL: ls_accept_tail_kernel<C><<<g.outer, 32, 0, st>>>(P, B, c, lc, cur); break;
+        case LS_PHASE_RESIDENT: ls_resident_variant<C>(g.res_minb)<<<grp, g.res_threads, g.res_smem, st>>>(P, B, c, lc, cur); break;
     }
 }
 

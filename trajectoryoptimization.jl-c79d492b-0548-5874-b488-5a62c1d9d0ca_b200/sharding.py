@@ -13,6 +13,24 @@ def shard_range(B_total, rank, world):
     return b0, min(B_total, b0 + per)
 
 
+def shard_indices(B_total, rank, world, interleaved=False):
+    """Global problem indices owned by `rank`: the contiguous slice of shard_range, or -- to spread the few long-running
+    problems of a batch over the GPUs -- every world-th problem starting at `rank`."""
+    if interleaved:
+        return np.arange(rank, B_total, world)
+    b0, b1 = shard_range(B_total, rank, world)
+    return np.arange(b0, b1)
+
+
+def unshard(parts, B_total, world, interleaved=False):
+    """Inverse of shard_indices: per-rank arrays (rank order) -> one array in global problem order."""
+    out = np.zeros((B_total,) + parts[0].shape[1:], dtype=parts[0].dtype)
+    for r, part in enumerate(parts):
+        idx = shard_indices(B_total, r, world, interleaved)
+        out[idx] = part[: len(idx)]
+    return out
+
+
 def allgather_results(local_records, dist, device=None):
     """All-gather the structured result records of every rank (ragged shards are padded).
     `dist` is torch.distributed (nccl on GPU, gloo in the CPU tests)."""
