@@ -39,6 +39,7 @@ for step in "$@"; do
             timeout 900 ncu --set full --clock-control none --import-source on -k regex:'ls_resident_kernel' -c 1 -f -o $OUT/${TAG}_prof_resident \
                 python tools/resident_profile.py quad_altro 8 > $OUT/${TAG}_ncu_resident.log 2>&1
             echo "ncu resident exit $?" ;;
+    bpprof) timeout 300 python tools/bp_profile.py 8192 > $OUT/${TAG}_bp_profile.log 2>&1; echo "bpprof exit $?"; cat $OUT/${TAG}_bp_profile.log ;;
     env=*)  export "${step#env=}" ;;
     tag=*)  TAG="${step#tag=}" ;;
     *) echo "unknown step $step" ;;
