@@ -20,7 +20,7 @@ assert lib.to_debug_enable(bs.h, 64) == 0
 bs.solve(opts)
 buf = np.zeros(64, dtype=np.int64)
 assert lib.to_debug_read(bs.h, buf.ctypes.data, 64) == 0
-names = ["wait+sync", "expansion", "phaseA T=A'S", "phaseB Q+=TA", "publish+sync", "chol+LU", "solves+KQ+sync", "S update+sync", "sym+dV"]
+names = ["wait+sync", "phaseA T=A'S", "phaseB T*A", "expansion + Q add", "publish+sync+prefetch", "chol+LU", "solves+KQ+sync", "S update+sync", "sym+dV"]
 tot = buf[:9].sum()
 ticks = C.c_int32()
 lib.to_debug_ticks(bs.h, C.byref(ticks))

@@ -201,9 +201,9 @@ int build_variant(TOSolver* s, int which, const TOALTROOptions* ao) {
     if ((rc = upload(s, v, s->qf, &P.qf))) return rc;
     // rows per knot (expanded; identical knots share storage through the class table)
     std::vector<DevRow> rows;
-    std::vector<int> kb(N), kc(N), lo(N + 1);
+    std::vector<int> kb(N), kc(N), lo(N + 1), kcols(N, -1), col_tab;
     // cache per (class, position-kind) to keep the row table small: kind 0 = first knot, 1 = interior, 2 = terminal
-    struct Key { int cls, pos; int begin, count; };
+    struct Key { int cls, pos; int begin, count; int cols; };
     std::vector<Key> cache;
     int off = 0;
     for (int k = 0; k < N; k++) {
@@ -258,13 +258,30 @@ int build_variant(TOSolver* s, int which, const TOALTROOptions* ao) {
                     out.push_back(r);
                 }
             }
-            Key key2{cls, pos, (int)rows.size(), (int)out.size()};
+            // per-column row lists of a set made of one-entry rows only (at most 4 rows per column)
+            int cols_off = -1;
+            {
+                const int nz = nbar + mbar;
+                std::vector<int> tab((size_t)nz * 4, -1), cnt(nz, 0);
+                bool ok = !out.empty();
+                for (size_t i = 0; i < out.size() && ok; i++) {
+                    const DevRow& r = out[i];
+                    if (r.kind != DR_LIN || r.col < 0 || r.col >= nz || cnt[r.col] >= 4) { ok = false; break; }
+                    tab[(size_t)r.col * 4 + cnt[r.col]++] = (int)i;
+                }
+                if (ok) {
+                    cols_off = (int)col_tab.size();
+                    col_tab.insert(col_tab.end(), tab.begin(), tab.end());
+                }
+            }
+            Key key2{cls, pos, (int)rows.size(), (int)out.size(), cols_off};
             rows.insert(rows.end(), out.begin(), out.end());
             cache.push_back(key2);
             found = (int)cache.size() - 1;
         }
         kb[k] = cache[found].begin;
         kc[k] = cache[found].count;
+        kcols[k] = cache[found].cols;
         lo[k] = off;
         off += kc[k];
     }
@@ -275,6 +292,8 @@ int build_variant(TOSolver* s, int which, const TOALTROOptions* ao) {
     if ((rc = upload(s, v, kb, &P.knot_row_begin))) return rc;
     if ((rc = upload(s, v, kc, &P.knot_row_count))) return rc;
     if ((rc = upload(s, v, lo, &P.knot_lam_off))) return rc;
+    if ((rc = upload(s, v, kcols, &P.knot_cols))) return rc;
+    if ((rc = upload(s, v, col_tab, &P.col_tab))) return rc;
     v.built = true;
     return 0;
 }

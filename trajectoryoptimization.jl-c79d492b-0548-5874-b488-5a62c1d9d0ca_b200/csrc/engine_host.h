@@ -28,6 +28,11 @@ struct DevProblem {
     const int* knot_row_begin;  // N entries: first row of knot k in rows[]
     const int* knot_row_count;  // N entries
     const int* knot_lam_off;    // N+1 entries: offset of knot k in the per-problem λ/μ arrays
+    // knots whose rows are all of the one-entry kind (bounds, goal, slack equality): per column of [x;u] the (at most 4) rows
+    // that touch it, so a lane evaluates only its own rows.  knot_cols[k] = offset of the knot's table in col_tab ((n+m) x 4
+    // row indices relative to the knot's first row, ascending, -1 = none), or -1: evaluate row by row (lockstep.cuh expansion)
+    const int* knot_cols;       // N entries
+    const int* col_tab;
 };
 
 struct DevBatch {

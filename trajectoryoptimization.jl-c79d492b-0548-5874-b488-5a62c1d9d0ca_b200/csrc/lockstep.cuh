@@ -205,7 +205,7 @@ struct LsSolver : Solver<C> {
 // DevProblem fields (generic pointers into shared memory).
 constexpr int LS_ROWCAP = 256;  // 14 KB of constraint rows (car_escape: ~190 distinct rows)
 __host__ __device__ inline int ls_tab_bytes(int N, int nrows) {
-    const int tab = ((3 * N + 1) * 4 + 15) & ~15;
+    const int tab = ((4 * N + 1) * 4 + 15) & ~15;
     return tab + ((nrows <= LS_ROWCAP) ? nrows * (int)sizeof(DevRow) : 0);
 }
 __device__ inline void ls_stage_problem(DevProblem& Pl, const DevProblem& P, unsigned char* smem_tab) {
@@ -216,11 +216,13 @@ __device__ inline void ls_stage_problem(DevProblem& Pl, const DevProblem& P, uns
         tab[N + i] = P.knot_row_count[i];
     }
     for (int i = threadIdx.x; i <= N; i += blockDim.x) tab[2 * N + i] = P.knot_lam_off[i];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) tab[3 * N + 1 + i] = P.knot_cols[i];
     Pl.knot_row_begin = tab;
     Pl.knot_row_count = tab + N;
     Pl.knot_lam_off = tab + 2 * N;
+    Pl.knot_cols = tab + 3 * N + 1;
     if (P.nrows <= LS_ROWCAP) {
-        DevRow* rows = reinterpret_cast<DevRow*>(smem_tab + (((3 * N + 1) * 4 + 15) & ~15));
+        DevRow* rows = reinterpret_cast<DevRow*>(smem_tab + (((4 * N + 1) * 4 + 15) & ~15));
         for (int i = threadIdx.x; i < P.nrows; i += blockDim.x) rows[i] = P.rows[i];
         Pl.rows = rows;
     }
@@ -440,6 +442,24 @@ struct alignas(16) BpExpSmem {
     double xu[XU], vQx[C::nq], vQu[C::mq];
 };
 
+// a / d from the correctly rounded reciprocal y = 1/d (an IEEE division done once, off the dependent chain) and two
+// Newton-Markstein corrections: q1 is a faithful quotient, so r1 = a - d*q1 is exact and q2 = RN(a/d) by Markstein's theorem.
+// BITWISE equal to a / d for operands in the safe exponent range (2^-300 .. 2^300, checked on 4.5e9 random and structured pairs
+// by tools/check_divby.c); zeros keep their sign through q0; everything else (subnormal, huge, inf, nan, d = 0) takes the true
+// division.  Five dependent FMAs (~45 cycles) instead of a DDIV (~126): the back-substitution of the LU solve divides by the
+// pivots one after the other, and their reciprocals exist already (the factorisation scales the L column by them).
+__device__ __forceinline__ double div_by(double a, double d, double y) {
+    const unsigned ea = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu, ed = ((unsigned)__double2hiint(d) >> 20) & 0x7ffu;
+    const bool safe = (ed - 723u <= 600u) && ((ea - 723u <= 600u) || a == 0.0);
+    if (!safe) return a / d;
+    const double q0 = a * y;
+    const double r0 = fma(-d, q0, a);
+    const double q1 = fma(r0, y, q0);
+    const double r1 = fma(-d, q1, a);
+    const double q2 = fma(r1, y, q1);
+    return (a == 0.0) ? q0 : q2;
+}
+
 template <class C, class SM = BpSmem<C>>
 struct BpGroup {
     static constexpr int n = C::n, m = C::m, n0 = C::n0, m0 = C::m0, nq = C::nq, mq = C::mq;
@@ -569,6 +589,37 @@ struct BpGroup {
         for (int i = 0; i < n; i++) Qxxc[i] = 0.0;
 #pragma unroll
         for (int i = 0; i < m; i++) { Quxc[i] = 0.0; Quuc[i] = 0.0; }
+        const int ct = has_al ? P.knot_cols[k] : -1;
+        if (ct >= 0) {
+            // every row of this knot has ONE +-1 entry (bounds, goal, slack equality): the lane walks the rows of its own
+            // columns only (x_j, u_j), in row order -- the same sums as the row-by-row loop below, where each row is one
+            // lane's work while the others wait (quadrotor: 4 of 505 warp instructions per knot were useful there)
+            auto own = [&](const int r_, const double z, double& dd, double& aa) {
+                if (r_ < 0) return;
+                const DevRow* r = &P.rows[rb + r_];
+                const double sg = r->sign, ra = r->a;
+                const int req = r->eq;
+                const double c = (sg > 0) ? (z - ra) : (ra - z);
+                const double lam_r = lams[r_];
+                const bool act = req ? true : ((c >= 0.0) || (lam_r > 0.0));
+                const double im = act ? mus[r_] : 0.0;
+                const double g = im * c + lam_r;
+                const double gj = (sg > 0) ? 1.0 : -1.0;
+                dd = fma(gj * im, gj, dd);
+                aa = fma(gj, g, aa);
+            };
+            const int4* tab4 = reinterpret_cast<const int4*>(P.col_tab + ct);
+            if (j < n) {
+                const int4 sl = __ldg(tab4 + j);
+                const double z = xs[j];
+                own(sl.x, z, dxx, ax); own(sl.y, z, dxx, ax); own(sl.z, z, dxx, ax); own(sl.w, z, dxx, ax);
+            }
+            if (!term && j < m) {
+                const int4 sl = __ldg(tab4 + n + j);
+                const double z = xs[n + j];
+                own(sl.x, z, duu, au); own(sl.y, z, duu, au); own(sl.z, z, duu, au); own(sl.w, z, duu, au);
+            }
+        } else
         for (int r_ = 0; r_ < rc; r_++) {
             const DevRow r = P.rows[rb + r_];
             if (r.kind == DR_LIN) {
@@ -822,6 +873,7 @@ struct BpGroup {
     }
     struct LU {
         double a[m * m];
+        double rp[m];   // 1 / pivot (general path only): correctly rounded reciprocals, reused by lu_solve through div_by
         int piv[m];
         bool tril_only, triu;
     };
@@ -882,6 +934,7 @@ struct BpGroup {
                 }
             }
             const double rp = 1.0 / f.a[c * m + c];
+            f.rp[c] = rp;
 #pragma unroll
             for (int i = c + 1; i < m; i++) f.a[c * m + i] = f.a[c * m + i] * rp;
         }
@@ -916,12 +969,22 @@ struct BpGroup {
                 bv[i] = bv[i] - acc;
             }
         }
+        if (f.triu) {  // triangular input (always so for m = 1): no factorisation ran, plain divisions
+#pragma unroll
+            for (int i = m - 1; i >= 0; i--) {
+                double acc = 0.0;
+#pragma unroll
+                for (int l = i + 1; l < m; l++) acc = fma(f.a[l * m + i], bv[l], acc);
+                bv[i] = (bv[i] - acc) / f.a[i * m + i];
+            }
+            return;
+        }
 #pragma unroll
         for (int i = m - 1; i >= 0; i--) {
             double acc = 0.0;
 #pragma unroll
             for (int l = i + 1; l < m; l++) acc = fma(f.a[l * m + i], bv[l], acc);
-            bv[i] = (bv[i] - acc) / f.a[i * m + i];
+            bv[i] = div_by(bv[i] - acc, f.a[i * m + i], f.rp[i]);
         }
     }
 
@@ -1072,24 +1135,45 @@ struct BpGroup {
                 lu_factor(f);
                 if (!pd) { failed = true; break; }
                 tick(5);
-                if (j < n) {
-                    double rhs[m];
+                if constexpr (n < GS) {
+                    // lanes 0..n-1 solve for their column of K, lane n for the feed-forward term d: ONE pass through the
+                    // triangular solves (two divergent passes cost a second ~600-cycle dependent chain per knot)
+                    if (j <= n) {
+                        double rhs[m];
 #pragma unroll
-                    for (int i = 0; i < m; i++) rhs[i] = Quxc[i];
-                    lu_solve(f, rhs);
+                        for (int i = 0; i < m; i++) rhs[i] = (j < n) ? Quxc[i] : sm.Qu[i];
+                        lu_solve(f, rhs);
+                        if (j < n) {
 #pragma unroll
-                    for (int i = 0; i < m; i++) {
-                        Kcol[i] = -1.0 * rhs[i];
-                        sm.KT[i * LDn + j] = Kcol[i];
+                            for (int i = 0; i < m; i++) {
+                                Kcol[i] = -1.0 * rhs[i];
+                                sm.KT[i * LDn + j] = Kcol[i];
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < m; i++) sm.d[i] = -1.0 * rhs[i];
+                        }
                     }
-                }
-                if (j == DL) {
-                    double rhs[m];
+                } else {
+                    if (j < n) {
+                        double rhs[m];
 #pragma unroll
-                    for (int i = 0; i < m; i++) rhs[i] = sm.Qu[i];
-                    lu_solve(f, rhs);
+                        for (int i = 0; i < m; i++) rhs[i] = Quxc[i];
+                        lu_solve(f, rhs);
 #pragma unroll
-                    for (int i = 0; i < m; i++) sm.d[i] = -1.0 * rhs[i];
+                        for (int i = 0; i < m; i++) {
+                            Kcol[i] = -1.0 * rhs[i];
+                            sm.KT[i * LDn + j] = Kcol[i];
+                        }
+                    }
+                    if (j == DL) {
+                        double rhs[m];
+#pragma unroll
+                        for (int i = 0; i < m; i++) rhs[i] = sm.Qu[i];
+                        lu_solve(f, rhs);
+#pragma unroll
+                        for (int i = 0; i < m; i++) sm.d[i] = -1.0 * rhs[i];
+                    }
                 }
                 // KQ = K'Quu (row j)
                 double KQr[m];
@@ -1314,17 +1398,38 @@ struct alignas(16) BpCtaSmem {
     double K[n * LDm];     // (i,j) at [j*LDm+i]
     double KQ[m * LDn];    // (K'Quu)(i,c) at [c*LDn+i]
     double Quu[m * m], Qx[n], Qu[m], d[m], Sx[n], accA[n], accB[m];
+    double QuuC[m * m];    // overlap schedule: the PD-test warp's own copy of Quu
     int pd;
 };
+
+// Overlap schedule of the CTA pass (blocks of 256 threads, i.e. the quadrotor): the m x m factorisation chain (four dependent
+// reciprocals, ~900 cycles) starts as soon as Quu = Quu_k + (B'S)B exists -- warp 0 computes those 16 elements itself -- and runs
+// BESIDE the n x n products of the other warps instead of after them; the PD test does the same on warp 1; the symmetrisation is
+// folded into the cost-to-go update (each thread forms S'(i,j) and S'(j,i)).  Three block barriers and one producer/consumer
+// named barrier per knot instead of five block barriers with the factorisation alone between two of them.
+template <class C, int NT> __host__ __device__ constexpr bool ls_bp_cta_overlap() {
+    return NT == 256 && (C::n * C::n + C::m * C::n) <= (NT - 64) + 32 && C::m * C::m <= 16 && C::n < 31 && C::m > 1;
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_sync_n(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // the backward pass of ONE problem by the whole CTA (NT threads; every thread of the block must call it)
 template <class C, int NT>
 __device__ __forceinline__ void ls_bp_cta_problem(const DevProblem& P, const TOiLQROptions& io, double* ws, const WsLayout& L,
-                                                  BpCtaSmem<C>& sm, LsState* st, const int tid) {
+                                                  BpCtaSmem<C>& sm, LsState* st, const int tid, long long* prof = nullptr) {
     constexpr int n = C::n, m = C::m, LDZ = C::LDZ;
     constexpr int LDn = BpCtaSmem<C>::LDn, LDm = BpCtaSmem<C>::LDm;
     typedef typename BpGroup<C>::LU LU;
     const int N = P.N;
+    // optional cycle profile (thread 0 of the profiled CTA; diagnostics): cycles per section of the knot loop
+    long long pt0 = prof ? clock64() : 0;
+    auto ptick = [&](int section) {
+        if (prof) {
+            const long long t = clock64();
+            prof[section] += t - pt0;
+            pt0 = t;
+        }
+    };
     {
         double rho = st->rho, drho = st->drho;  // uniform over the CTA
         auto reg_update = [&](bool increase) {  // ilqr_methods.jl:164-176
@@ -1359,8 +1464,10 @@ __device__ __forceinline__ void ls_bp_cta_problem(const DevProblem& P, const TOi
             bool failed = false;
             for (int k = N - 2; k >= 0; k--) {
                 const int buf = k & 1;
+                ptick(0);
                 cp_async_wait_all();
                 __syncthreads();  // knot k's inputs have landed; S, Sx of knot k+1 are complete
+                ptick(1);
                 if (k > 0) prefetch(k - 1, buf ^ 1);
                 const double* AB = sm.AB[buf];
                 const double* Qk = sm.Q[buf];
@@ -1388,9 +1495,167 @@ __device__ __forceinline__ void ls_bp_cta_problem(const DevProblem& P, const TOi
                     for (int l = 0; l < n; l++) acc = fma(AB[l * LDZ + c], V[l], acc);
                     *out = acc;
                 }
+                ptick(2);
                 __syncthreads();
-                // ---- step 2: Q = Q[k] + (T*A, Tu*A, Tu*B, A'Sx, B'Sx); restart mode writes the sums back (quirk Q1)
+                ptick(3);
                 double* qg = ws + L.QST + (size_t)k * C::QS;
+                if constexpr (ls_bp_cta_overlap<C, NT>()) {
+                    const int warp = tid >> 5, lane = tid & 31;
+                    // ---- step 2 (overlap schedule): one "row of T / Tu dot column of [A B]" task per thread
+                    {
+                        constexpr int NBIG = m * n + n * n;  // Qux first (the solves wait for it), then Qxx
+                        int g = -1, e = -1;
+                        if (warp >= 2) g = tid - 64;
+                        else if (lane >= 16) g = (NT - 64) + warp * 16 + (lane - 16);
+                        else e = lane;  // warps 0 and 1, lanes 0..15: Quu (both warps: each feeds its own factorisation)
+                        const double* Lp = nullptr;
+                        double* out = nullptr;
+                        int ld = 0, c = 0, qi = 0;
+                        bool glob = store_mode;
+                        if (g >= 0 && g < m * n) {
+                            const int i = g % m, j = g / m;
+                            Lp = &sm.Tu[i]; ld = LDm; c = j; qi = n + m + n * n + m * m + g; out = &sm.Qux[j * LDm + i];
+                        } else if (g >= m * n && g < NBIG) {
+                            const int t = g - m * n, i = t % n, j = t / n;
+                            Lp = &sm.T[i]; ld = LDn; c = j; qi = n + m + t; out = &sm.Qxx[j * LDn + i];
+                        } else if (e >= 0 && e < m * m) {
+                            const int i = e % m, j = e / m;
+                            Lp = &sm.Tu[i]; ld = LDm; c = n + j; qi = n + m + n * n + e;
+                            out = (warp == 0) ? &sm.Quu[j * m + i] : &sm.QuuC[j * m + i];
+                            glob = store_mode && warp == 0;
+                        }
+                        if (out) {
+                            double acc = 0.0;
+#pragma unroll
+                            for (int l = 0; l < n; l++) acc = fma(Lp[l * ld], AB[l * LDZ + c], acc);
+                            const double v = Qk[qi] + acc;
+                            *out = v;
+                            if (glob) qg[qi] = v;
+                        }
+                    }
+                    ptick(4);
+                    if (warp >= 2) {
+                        bar_arrive(2, NT - 32);  // Qux (and Qxx) of this warp are in shared memory
+                    } else if (warp == 0) {
+                        if (lane < n) {
+                            const double v = Qk[lane] + sm.accA[lane];
+                            sm.Qx[lane] = v;
+                            if (store_mode) qg[lane] = v;
+                        }
+                        if (lane < m) {
+                            const double v = Qk[n + lane] + sm.accB[lane];
+                            sm.Qu[lane] = v;
+                            if (store_mode) qg[n + lane] = v;
+                        }
+                        __syncwarp();
+                        LU f;
+                        if (lane <= n) {
+#pragma unroll
+                            for (int q = 0; q < m * m; q++) f.a[q] = sm.Quu[q];
+#pragma unroll
+                            for (int i = 0; i < m; i++) f.a[i * m + i] = sm.Quu[i * m + i] + rho * 1.0;
+                            BpGroup<C>::lu_factor(f);
+                        }
+                        ptick(5);
+                        bar_sync_n(2, NT - 32);  // Qux of the other warps has arrived
+                        ptick(6);
+                        if (lane <= n) {
+                            double rhs[m];
+#pragma unroll
+                            for (int i = 0; i < m; i++) rhs[i] = (lane < n) ? sm.Qux[lane * LDm + i] : sm.Qu[i];
+                            BpGroup<C>::lu_solve(f, rhs);
+                            if (lane < n) {
+                                double Kc[m];
+#pragma unroll
+                                for (int i = 0; i < m; i++) {
+                                    Kc[i] = -1.0 * rhs[i];
+                                    sm.K[lane * LDm + i] = Kc[i];
+                                }
+#pragma unroll
+                                for (int c = 0; c < m; c++) {  // KQ = K'Quu (row `lane`)
+                                    double acc = 0.0;
+#pragma unroll
+                                    for (int l = 0; l < m; l++) acc = fma(Kc[l], sm.Quu[c * m + l], acc);
+                                    sm.KQ[c * LDn + lane] = acc;
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < m; i++) sm.d[i] = -1.0 * rhs[i];
+                            }
+                        }
+                    } else {  // warp 1: isposdef(Hermitian(Quu_reg))
+                        __syncwarp();
+                        if (lane == 0) {
+                            double A_[m * m];
+#pragma unroll
+                            for (int q = 0; q < m * m; q++) A_[q] = sm.QuuC[q];
+#pragma unroll
+                            for (int i = 0; i < m; i++) A_[i * m + i] = sm.QuuC[i * m + i] + rho * 1.0;
+                            sm.pd = BpGroup<C>::chol_pd(A_) ? 1 : 0;
+                        }
+                    }
+                    ptick(7);
+                    __syncthreads();
+                    ptick(8);
+                    if (!sm.pd) { failed = true; break; }
+                    // ---- steps 4 + 5: gains out, symmetrised cost-to-go, dV
+                    {
+                        double* kd = ws + L.KD + (size_t)k * C::KDS;
+                        for (int t = tid; t < n * n + n + m * n + m + 1; t += NT) {
+                            if (t < n * n) {  // S.xx(i,j) = 0.5 (S'(i,j) + S'(j,i)),  S' = Qxx + KQ*K + K'Qux + Qux'K
+                                const int i = t % n, j = t / n;
+                                double b1 = 0.0, b2 = 0.0, b3 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+#pragma unroll
+                                for (int l = 0; l < m; l++) {
+                                    const double kj = sm.K[j * LDm + l], qj = sm.Qux[j * LDm + l];
+                                    const double ki = sm.K[i * LDm + l], qi_ = sm.Qux[i * LDm + l];
+                                    b1 = fma(sm.KQ[l * LDn + i], kj, b1);
+                                    b2 = fma(ki, qj, b2);
+                                    b3 = fma(qi_, kj, b3);
+                                    c1 = fma(sm.KQ[l * LDn + j], ki, c1);
+                                    c2 = fma(kj, qi_, c2);
+                                    c3 = fma(qj, ki, c3);
+                                }
+                                const double sij = ((sm.Qxx[j * LDn + i] + b1) + b2) + b3;
+                                const double sji = ((sm.Qxx[i * LDn + j] + c1) + c2) + c3;
+                                sm.S[j * LDn + i] = 0.5 * (sij + sji);
+                            } else if (t < n * n + n) {  // S.x = Qx + KQ d + K'Qu + Qux'd
+                                const int j = t - n * n;
+                                double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                                for (int l = 0; l < m; l++) a1 = fma(sm.KQ[l * LDn + j], sm.d[l], a1);
+#pragma unroll
+                                for (int l = 0; l < m; l++) a2 = fma(sm.K[j * LDm + l], sm.Qu[l], a2);
+#pragma unroll
+                                for (int l = 0; l < m; l++) a3 = fma(sm.Qux[j * LDm + l], sm.d[l], a3);
+                                sm.Sx[j] = ((sm.Qx[j] + a1) + a2) + a3;
+                            } else if (t < n * n + n + m * n) {
+                                const int e = t - n * n - n;  // kd[j*m+i] = K(i,j)
+                                kd[e] = sm.K[(e / m) * LDm + (e % m)];
+                            } else if (t < n * n + n + m * n + m) {
+                                const int i = t - n * n - n - m * n;
+                                kd[m * n + i] = sm.d[i];
+                            }
+                        }
+                        if (tid == NT - 1) {  // dV
+                            double a_ = 0.0;
+#pragma unroll
+                            for (int l = 0; l < m; l++) a_ = fma(sm.d[l], sm.Qu[l], a_);
+                            dV0 += a_;
+                            double acc = 0.0;
+#pragma unroll
+                            for (int c = 0; c < m; c++) {
+                                double w = 0.0;
+#pragma unroll
+                                for (int l = 0; l < m; l++) w = fma(0.5 * sm.d[l], sm.Quu[c * m + l], w);
+                                acc = fma(w, sm.d[c], acc);
+                            }
+                            dV1 += acc;
+                        }
+                    }
+                    continue;  // the barrier at the top of the next knot separates this update from its readers
+                }
+                // ---- step 2: Q = Q[k] + (T*A, Tu*A, Tu*B, A'Sx, B'Sx); restart mode writes the sums back (quirk Q1)
                 for (int t = tid; t < n * n + m * n + m * m + n + m; t += NT) {
                     if (t < n * n + m * n + m * m) {  // "row i of T or Tu dot column c of [A B]": one code path
                         const double* Lp;
@@ -2190,16 +2455,14 @@ template <class C> LsBpFn ls_bp_variant(int minb) {
     return ls_bp_kernel<C, LS_BP_WARPS, 3>;
 }
 template <class C> LsJacFn ls_jac_variant(int pc, int minb) {
-    if constexpr (C::MODEL == 4) {
-        if (pc == 1) return minb == 4 ? ls_jac_kernel<C, 1, 4> : (minb == 3 ? ls_jac_kernel<C, 1, 3> : ls_jac_kernel<C, 1, 2>);
-        if (pc == 2) return minb == 4 ? ls_jac_kernel<C, 2, 4> : (minb == 3 ? ls_jac_kernel<C, 2, 3> : ls_jac_kernel<C, 2, 2>);
-    }
+    // quadrotor: one partial direction per thread at <= 168 registers (measured best, profiles/r01f; the other register-cap /
+    // chunking variants of round 1 were removed after the sweep -- they tripled the compile time of the instance)
+    if constexpr (C::MODEL == 4) return ls_jac_kernel<C, 1, 3>;
     return ls_jac_kernel<C, C::PC, 2>;
 }
 template <class C> LsTrialFn ls_trial_variant(int minb, bool all) {
     if constexpr (C::MODEL == 4) {
-        if (minb == 4) return all ? ls_trial_kernel<C, 32, 4> : ls_trial_kernel<C, LS_TRIAL_G, 4>;
-        if (minb == 1 && all) return ls_trial_kernel<C, 32, 1>;  // tail mode without a register cap (latency experiment)
+        if (all) return ls_trial_kernel<C, 32, 1>;  // tail mode: a latency chain of one warp per problem, no register cap (profiles/r01t1)
     }
     return all ? ls_trial_kernel<C, 32, 3> : ls_trial_kernel<C, LS_TRIAL_G, 3>;
 }
@@ -2211,10 +2474,6 @@ template <class C> constexpr int ls_bp_cta_threads() {
 }
 
 template <class C> LsBpFn ls_bp_cta_variant(int minb) {
-    if constexpr (C::MODEL == 4) {  // quadrotor: register-cap variants (occupancy of the latency path when it serves thousands of problems)
-        if (minb == 3) return ls_bp_cta_kernel<C, ls_bp_cta_threads<C>(), 3>;
-        if (minb == 4) return ls_bp_cta_kernel<C, ls_bp_cta_threads<C>(), 4>;
-    }
     return ls_bp_cta_kernel<C, ls_bp_cta_threads<C>(), 2>;
 }
 
@@ -2224,8 +2483,10 @@ template <class C> constexpr int ls_res_threads() {
 typedef void (*LsResFn)(const DevProblem, const DevBatch, const DevCtl, const LsCtl, const int);
 template <class C> LsResFn ls_resident_variant(int minb) {
     constexpr int JPC = (C::MODEL == 4) ? 1 : C::PC;  // partial directions per Jacobian item (values do not depend on the chunking)
-    if (minb == 2) return ls_resident_kernel<C, ls_res_threads<C>(), 2, JPC>;
-    return ls_resident_kernel<C, ls_res_threads<C>(), 1, JPC>;
+    if constexpr (C::MODEL == 4) {
+        if (minb == 1) return ls_resident_kernel<C, ls_res_threads<C>(), 1, JPC>;  // no register cap: half the resident CTAs, no spills
+    }
+    return ls_resident_kernel<C, ls_res_threads<C>(), 2, JPC>;
 }
 
 template <class C> unsigned long long ls_ws_doubles_fn(int N, int Ptot) { return ws_layout<C>(N, Ptot, false).total; }
@@ -2254,11 +2515,7 @@ template <class C> int ls_setup_fn(int sm_count, int N, int nrows, LsGrids* g) {
     if constexpr (C::MODEL == 4) {  // quadrotor: kernel variants selectable at run time (tuning)
         g->jac_pc = 1;    // measured (profiles/r01f): one partial direction per thread at <=168 registers (12 warps/SM)
         g->jac_minb = 3;  // beats two directions at 255 registers (8 warps/SM): 4.4 vs 5.4 ms per 16,384 problems
-        if (const char* env = getenv("TRAJOPT_B200_JAC_PC")) { const int v = atoi(env); if (v == 1 || v == 2) g->jac_pc = v; }
-        if (const char* env = getenv("TRAJOPT_B200_JAC_MINB")) { const int v = atoi(env); if (v >= 2 && v <= 4) g->jac_minb = v; }
-        if (const char* env = getenv("TRAJOPT_B200_TRIAL_MINB")) { const int v = atoi(env); if (v == 3 || v == 4) g->trial_minb = v; }
         g->trial_all_minb = 1;  // tail mode is a latency chain of one warp per problem: no register cap (0.377 -> 0.364 ms, profiles/r01t1)
-        if (const char* env = getenv("TRAJOPT_B200_TRIAL_ALL_MINB")) { const int v = atoi(env); if (v == 1 || v == 3 || v == 4) g->trial_all_minb = v; }
     }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_jac_variant<C>(g->jac_pc, g->jac_minb), 128, 0);
     g->jac = sm_count * (nb > 0 ? nb : 1);
@@ -2278,9 +2535,6 @@ template <class C> int ls_setup_fn(int sm_count, int N, int nrows, LsGrids* g) {
     g->expand = sm_count * (nb > 0 ? nb : 1);
     g->bp_cta_smem = (int)sizeof(BpCtaSmem<C>);
     g->bp_cta_minb = 2;
-    if constexpr (C::MODEL == 4) {
-        if (const char* env = getenv("TRAJOPT_B200_BP_CTA_MINB")) { const int v = atoi(env); if (v == 3 || v == 4) g->bp_cta_minb = v; }
-    }
     if (cudaFuncSetAttribute(ls_bp_cta_variant<C>(g->bp_cta_minb), cudaFuncAttributeMaxDynamicSharedMemorySize, g->bp_cta_smem) != cudaSuccess) return -5;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_bp_cta_variant<C>(g->bp_cta_minb), ls_bp_cta_threads<C>(), g->bp_cta_smem);
     g->occ_bp_cta = nb;

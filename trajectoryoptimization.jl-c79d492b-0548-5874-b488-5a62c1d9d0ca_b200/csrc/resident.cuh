@@ -52,9 +52,18 @@ __device__ __forceinline__ void res_role_barrier(int nthreads) {
 template <class C, int LO, int HI, int R>
 __device__ __forceinline__ void res_rollout_role(const DevProblem& P, const TOiLQROptions& io, const double* ws, const WsLayout& L,
                                                  ResTrialSmem<C>& ts, ResFlags& fl, double* XB, double* UB, const double* x0,
-                                                 const double alpha, const int t, const bool runs, const int role, const int wtid) {
+                                                 const double alpha, const int t, const bool runs, const int role, const int wtid,
+                                                 long long* prof = nullptr) {
     constexpr int n = C::n, m = C::m, CNT = HI - LO, SS = ResTrialSmem<C>::SS;
     const int N = P.N;
+    long long pt0 = prof ? clock64() : 0;
+    auto ptick = [&](int section) {  // diagnostics: cycles per section of the knot loop (thread 0 of the profiled CTA)
+        if (prof) {
+            const long long tt = clock64();
+            prof[section] += tt - pt0;
+            pt0 = tt;
+        }
+    };
     auto prefetch = [&](int k, int buf) {
         const double* xk = ws + L.X + (size_t)k * n;
         const double* uk = ws + L.U + (size_t)k * m;
@@ -84,6 +93,7 @@ __device__ __forceinline__ void res_rollout_role(const DevProblem& P, const TOiL
         const double* dk = Kk + m * n;
         double u[m];
         int badl = 0;
+        ptick(0);
         if (ok) {
             double x[n], dx[n], f[n];
 #pragma unroll
@@ -119,7 +129,9 @@ __device__ __forceinline__ void res_rollout_role(const DevProblem& P, const TOiL
                 ts.ex[xb ^ 1][LO + i][t] = xo[i] + k1[i] / 2.0;
             }
         }
+        ptick(1);
         res_role_barrier(R * 32);
+        ptick(2);
         if (ok) {
             double x[n], f[n];
 #pragma unroll
@@ -131,7 +143,9 @@ __device__ __forceinline__ void res_rollout_role(const DevProblem& P, const TOiL
                 ts.ex[xb][LO + i][t] = (xo[i] - k1[i]) + 2.0 * k2[i];
             }
         }
+        ptick(3);
         res_role_barrier(R * 32);
+        ptick(4);
         if (ok) {
             double x[n], f[n];
 #pragma unroll
@@ -152,8 +166,10 @@ __device__ __forceinline__ void res_rollout_role(const DevProblem& P, const TOiL
             if (bad || !(mx < io.max_state_value)) badl = 1;
         }
         ts.bad[k & 1][role][t] = badl;
+        ptick(5);
         cp_async_wait_all();
         res_role_barrier(R * 32);
+        ptick(6);
         xb ^= 1;
     }
     {
@@ -184,6 +200,123 @@ struct ResLayout {
 
 // doubles of per-CTA scratch in global memory: stage and AL cost of every (knot, step size) of the running line search
 __host__ __device__ inline size_t res_scratch_doubles(int N) { return 2 * (size_t)N * 32; }
+
+// ---- the phases of one iteration as separate (NOT inlined) functions: inlined into one kernel, the line search's live state
+// (13-element stage vectors per role) and the loop-invariant problem description left the register allocator so little room
+// that the 13-term products of the Riccati recursion were scheduled load -> use -> load -> use (profiles/r02e: 830 cycles for
+// a chain that needs ~250); with their own register allocation the phases are scheduled like the stand-alone kernels ----
+template <class C, int NT, int JPC>
+__device__ __noinline__ void res_phase_jac(const DevProblem& P, double* ws, const WsLayout& L, const int tid) {
+    constexpr int NCH = ls_jac_chunks<C, JPC>();
+    const int N = P.N;
+    for (int it = tid; it < (N - 1) * NCH; it += NT) {
+        const int k = it / NCH;
+        ls_jac_item<C, JPC>(P, ws, L, k, it - k * NCH);
+    }
+}
+
+template <class C, int NT>
+__device__ __noinline__ void res_phase_expand(const DevProblem& P, const TOiLQROptions& io, double* ws, const WsLayout& L,
+                                              BpExpSmem<C>* exsm, const bool al_on, const int tid) {
+    constexpr int n = C::n, m = C::m;
+    constexpr int GS = ls_group_size<C>();
+    constexpr int NG = NT / GS;
+    const int N = P.N;
+    const int lane = tid & 31;
+    const int g = tid / GS, j = tid % GS;
+    const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << (lane - j));
+    BpExpSmem<C>& es = exsm[g];
+    BpGroup<C, BpExpSmem<C>> G(P, es, ws, j, gmask, al_on, io);
+    G.load_cost_constants();
+    for (int k0 = 0; k0 < N; k0 += NG) {
+        const int k = k0 + g;
+        if (k < N) {
+            const double* xk = ws + L.X + (size_t)k * n;
+            __syncwarp(gmask);
+            if (k < N - 1) {
+                const double* uk = ws + L.U + (size_t)k * m;
+                for (int e = j; e < n + m; e += GS) es.xu[e] = (e < n) ? xk[e] : uk[e - n];
+            } else {
+                for (int e = j; e < n; e += GS) es.xu[e] = xk[e];
+            }
+            __syncwarp(gmask);
+            const int lo = P.knot_lam_off[k];
+            G.expansion(k, es.xu, ws + L.LAM + lo, ws + L.MU + lo);
+            if (k < N - 1) G.q_store(k);
+            else G.q_store_term(k);
+        }
+    }
+}
+
+template <class C, int NT>
+__device__ __noinline__ void res_phase_riccati(const DevProblem& P, const TOiLQROptions& io, double* ws, const WsLayout& L,
+                                               BpCtaSmem<C>& sm, LsState* st, const int tid, long long* prof) {
+    ls_bp_cta_problem<C, NT>(P, io, ws, L, sm, st, tid, prof);
+}
+
+// T1: state chains of all step sizes (lane = step size)
+template <class C, int NT>
+__device__ __noinline__ void res_phase_chains(const DevProblem& P, const TOiLQROptions& io, double* ws, const WsLayout& L,
+                                              ResTrialSmem<C>& ts, ResFlags& fl, double* stg, double* XB, double* UB, const double* x0g,
+                                              const int ntrial, const bool al_on, const int tid, long long* prof) {
+    constexpr int n = C::n;
+    constexpr int R = RollRoles<C>::R;
+    const int lane = tid & 31, warp = tid >> 5;
+    if (warp >= R) return;
+    double x0[n];
+#pragma unroll
+    for (int i = 0; i < n; i++) x0[i] = (i < C::n0) ? x0g[i] : 0.0;
+    const double alpha = __longlong_as_double((long long)(1023 - lane) << 52);  // 2^-lane
+    const bool runs = lane < ntrial;
+    if constexpr (RollRoles<C>::split) {
+        if (warp == 0) res_rollout_role<C, 0, 7, R>(P, io, ws, L, ts, fl, XB, UB, x0, alpha, lane, runs, 0, tid, prof);
+        else if (warp == 1) res_rollout_role<C, 7, 10, R>(P, io, ws, L, ts, fl, XB, UB, x0, alpha, lane, runs, 1, tid);
+        else res_rollout_role<C, 10, 13, R>(P, io, ws, L, ts, fl, XB, UB, x0, alpha, lane, runs, 2, tid);
+    } else {
+        const unsigned amask = __ballot_sync(0xffffffffu, runs);
+        bool ok = false;
+        if (runs) {
+            double Jt;
+            ok = Rollout<C>::template run_staged<true, 32, false>(P, io, ws, L, x0, alpha, al_on, Jt, XB, UB, lane, stg, lane,
+                                                                  __popc(amask), amask);
+        }
+        fl.okf[lane] = ok ? 1 : 0;
+    }
+}
+
+// T2: stage + AL cost of every (step size, knot) of the rollouts that stayed in the box, from the candidates
+template <class C, int NT>
+__device__ __noinline__ void res_phase_costs(const DevProblem& P, double* ws, const WsLayout& L, const ResFlags& fl, const double* XB,
+                                             const double* UB, double* cst, double* cal, const int ntrial, const bool al_on, const int tid) {
+    constexpr int n = C::n, m = C::m;
+    const int N = P.N;
+    const double* lam = ws + L.LAM;
+    const double* mu = ws + L.MU;
+    for (int it = tid; it < N * ntrial; it += NT) {
+        const int k = it / ntrial, t = it - k * ntrial;
+        if (!fl.okf[t]) continue;
+        double x[n], u[m];
+#pragma unroll
+        for (int i = 0; i < n; i++) x[i] = XB[cand_index((size_t)k * n + i, t, 32)];
+        double cs, ca = 0.0;
+        if (k < N - 1) {
+#pragma unroll
+            for (int i = 0; i < m; i++) u[i] = UB[cand_index((size_t)k * m + i, t, 32)];
+            cs = stage_cost<C>(P, x, u);
+            if (al_on) {
+                const int lo = P.knot_lam_off[k];
+                ca = knot_al_cost_at<C>(P, k, lam + lo, mu + lo, x, u);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < m; i++) u[i] = 0.0;
+            cs = term_cost<C>(P, x);
+            if (al_on) ca = knot_al_cost<C>(P, N - 1, lam, mu, x, u);
+        }
+        cst[k * 32 + t] = cs;
+        cal[k * 32 + t] = ca;
+    }
+}
 
 template <class C, int NT, int MINB, int JPC>
 __global__ void __launch_bounds__(NT, MINB) ls_resident_kernel(const DevProblem Pg, const DevBatch Bt, const DevCtl ctl, const LsCtl lc,
@@ -223,11 +356,14 @@ __global__ void __launch_bounds__(NT, MINB) ls_resident_kernel(const DevProblem 
         const int b = lc.list[cur][a];
         LsState* st = &lc.st[b];
         double* ws = lc.ws + (size_t)b * lc.ws_stride;
-        double x0[n];
-#pragma unroll
-        for (int i = 0; i < n; i++) x0[i] = (i < C::n0) ? Bt.x0[(size_t)b * C::n0 + i] : 0.0;
         // optional cycle profile (diagnostics: to_debug_enable): thread 0 of CTA 0 accumulates the cycles of every phase
         long long* prof = (ctl.debug && blockIdx.x == 0 && tid == 0) ? reinterpret_cast<long long*>(ctl.debug) + 16 : nullptr;
+        // the per-knot sub-profiles of the Riccati recursion / the state chain accumulate in SHARED memory (a global
+        // read-modify-write per section would put an L2 round trip on the very chain that is being measured)
+        __shared__ long long pacc[32];
+        if (prof) {
+            for (int i = 0; i < 32; i++) pacc[i] = 0;
+        }
         long long pt0 = prof ? clock64() : 0;
         auto ptick = [&](int section) {
             if (prof) {
@@ -239,100 +375,25 @@ __global__ void __launch_bounds__(NT, MINB) ls_resident_kernel(const DevProblem 
         for (;;) {  // one iLQR iteration of this problem
             if (prof) prof[15] += 1;
             // ---- Jacobians ----
-            for (int it = tid; it < (N - 1) * NCH; it += NT) {
-                const int k = it / NCH;
-                ls_jac_item<C, JPC>(P, ws, L, k, it - k * NCH);
-            }
+            res_phase_jac<C, NT, JPC>(P, ws, L, tid);
             __syncthreads();
             ptick(0);
             // ---- cost / constraint expansion of every knot into the Q trajectory ----
-            {
-                const int g = tid / GS, j = tid % GS;
-                const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << (lane - j));
-                BpExpSmem<C>& es = exsm[g];
-                BpGroup<C, BpExpSmem<C>> G(P, es, ws, j, gmask, al_on, io);
-                G.load_cost_constants();
-                for (int k0 = 0; k0 < N; k0 += NG) {
-                    const int k = k0 + g;
-                    if (k < N) {
-                        const double* xk = ws + L.X + (size_t)k * n;
-                        __syncwarp(gmask);
-                        if (k < N - 1) {
-                            const double* uk = ws + L.U + (size_t)k * m;
-                            for (int e = j; e < n + m; e += GS) es.xu[e] = (e < n) ? xk[e] : uk[e - n];
-                        } else {
-                            for (int e = j; e < n; e += GS) es.xu[e] = xk[e];
-                        }
-                        __syncwarp(gmask);
-                        const int lo = P.knot_lam_off[k];
-                        G.expansion(k, es.xu, ws + L.LAM + lo, ws + L.MU + lo);
-                        if (k < N - 1) G.q_store(k);
-                        else G.q_store_term(k);
-                    }
-                }
-            }
+            res_phase_expand<C, NT>(P, io, ws, L, exsm, al_on, tid);
             __syncthreads();
             ptick(1);
             // ---- Riccati recursion ----
-            ls_bp_cta_problem<C, NT>(P, io, ws, L, bpsm, st, tid);
+            res_phase_riccati<C, NT>(P, io, ws, L, bpsm, st, tid, prof ? pacc : nullptr);
             __syncthreads();
             ptick(2);
             const int bp_fail = st->bp_fail;
             const double dV0 = st->dV0, dV1 = st->dV1;
-            // ---- line search: state chains (T1) ----
             if (!bp_fail) {
-                const double alpha = __longlong_as_double((long long)(1023 - lane) << 52);  // 2^-lane
-                if constexpr (RollRoles<C>::split) {
-                    if (warp < R) {
-                        const bool runs = lane < ntrial;
-                        if (warp == 0) res_rollout_role<C, 0, 7, R>(P, io, ws, L, ts, fl, XB, UB, x0, alpha, lane, runs, 0, tid);
-                        else if (warp == 1) res_rollout_role<C, 7, 10, R>(P, io, ws, L, ts, fl, XB, UB, x0, alpha, lane, runs, 1, tid);
-                        else res_rollout_role<C, 10, 13, R>(P, io, ws, L, ts, fl, XB, UB, x0, alpha, lane, runs, 2, tid);
-                    }
-                } else {
-                    if (warp == 0) {
-                        const bool runs = lane < ntrial;
-                        const unsigned amask = __ballot_sync(0xffffffffu, runs);
-                        bool ok = false;
-                        if (runs) {
-                            double Jt;
-                            ok = Rollout<C>::template run_staged<true, 32, false>(P, io, ws, L, x0, alpha, al_on, Jt, XB, UB, lane, stg, lane,
-                                                                                  __popc(amask), amask);
-                        }
-                        fl.okf[lane] = ok ? 1 : 0;
-                    }
-                }
+                // ---- line search: state chains (T1), then costs (T2) ----
+                res_phase_chains<C, NT>(P, io, ws, L, ts, fl, stg, XB, UB, Bt.x0 + (size_t)b * C::n0, ntrial, al_on, tid, prof ? pacc + 16 : nullptr);
                 __syncthreads();
                 ptick(3);
-                // ---- T2: stage + AL cost of every (step size, knot) of the accepted-box rollouts, from the candidates ----
-                {
-                    const double* lam = ws + L.LAM;
-                    const double* mu = ws + L.MU;
-                    for (int it = tid; it < N * ntrial; it += NT) {
-                        const int k = it / ntrial, t = it - k * ntrial;
-                        if (!fl.okf[t]) continue;
-                        double x[n], u[m];
-#pragma unroll
-                        for (int i = 0; i < n; i++) x[i] = XB[cand_index((size_t)k * n + i, t, 32)];
-                        double cs, ca = 0.0;
-                        if (k < N - 1) {
-#pragma unroll
-                            for (int i = 0; i < m; i++) u[i] = UB[cand_index((size_t)k * m + i, t, 32)];
-                            cs = stage_cost<C>(P, x, u);
-                            if (al_on) {
-                                const int lo = P.knot_lam_off[k];
-                                ca = knot_al_cost_at<C>(P, k, lam + lo, mu + lo, x, u);
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < m; i++) u[i] = 0.0;
-                            cs = term_cost<C>(P, x);
-                            if (al_on) ca = knot_al_cost<C>(P, N - 1, lam, mu, x, u);
-                        }
-                        cst[k * 32 + t] = cs;
-                        cal[k * 32 + t] = ca;
-                    }
-                }
+                res_phase_costs<C, NT>(P, ws, L, fl, XB, UB, cst, cal, ntrial, al_on, tid);
                 __syncthreads();
                 ptick(4);
             }
@@ -432,6 +493,9 @@ __global__ void __launch_bounds__(NT, MINB) ls_resident_kernel(const DevProblem 
             __syncthreads();
             ptick(7);
             if (!fl.cont) break;
+        }
+        if (prof) {
+            for (int i = 0; i < 32; i++) { prof[32 + i] += pacc[i]; pacc[i] = 0; }
         }
         __syncthreads();
     }
