@@ -134,6 +134,14 @@ typedef struct TOALTROOptions {         /* src/solvers/altro/altro_solver.jl:6-6
     double  R_minimum_time;                   /* 1 */
     double  dt_max;                           /* 1 */
     double  dt_min;                           /* 1e-3 */
+    /* projected-Newton polish after the AL solve (altro_methods.jl:6-14,31-39; src/solvers/direct/projected_newton.jl,
+     * solve_type = :feasible).  With projected_newton != 0 the AL phase stops at projected_newton_tolerance (or, if that is
+     * negative, at the maximum penalty), then every problem is projected onto dynamics + active constraints. */
+    int32_t projected_newton;                 /* 0 */
+    int32_t pn_n_steps;                       /* 1     opts_pn.n_steps (direct_solvers.jl:19) */
+    double  projected_newton_tolerance;       /* 1e-3 */
+    double  pn_feasibility_tolerance;         /* 1e-6  opts_pn.feasibility_tolerance (direct_solvers.jl:28) */
+    double  pn_active_set_tolerance;          /* 1e-3  opts_pn.active_set_tolerance (direct_solvers.jl:25) */
 } TOALTROOptions;
 
 /* ---- per-problem result record (32 bytes; this is what the multi-GPU allgather exchanges) -- */
@@ -143,6 +151,11 @@ typedef struct TOALTROOptions {         /* src/solvers/altro/altro_solver.jl:6-6
 #define TO_STATUS_NOT_PD_SQRT    4  /* stage Hessian not PD in cost_expansion_sqrt! (objective.jl:76-93); aborted */
 #define TO_STATUS_MAX_OUTER      8  /* AL iterations exhausted with c_max >= constraint_tolerance */
 #define TO_STATUS_TRACE_TRUNC   16  /* history buffers were too small; records dropped */
+#define TO_STATUS_PN_FAILED     64  /* projected Newton: the reference would have thrown (a full step that does not reduce the
+                                       violation hits `count += a`, projected_newton.jl:304; or S + rho I not positive definite);
+                                       X, U keep the AL solution */
+#define TO_STATUS_PN_SKIPPED   128  /* projected Newton: a knot has more active constraint rows than the device block factor
+                                       holds (24); X, U keep the AL solution */
 #define TO_STATUS_REG_DIVERGED  32  /* backward pass: the PD test still fails with a non-finite regularisation rho
                                        (Quu is NaN).  The reference only warns on bp_reg_max (ilqr_methods.jl:169-171)
                                        and would restart forever (backward_pass.jl:52-63); the solve is aborted instead */
@@ -212,7 +225,7 @@ int to_set_trace(TOHandle h, int32_t inner_capacity, int32_t outer_capacity);
 /* The three solver entry points (blocking: return after the device work has finished). */
 int to_solve_ilqr(TOHandle h, const TOiLQROptions *o);   /* ilqr_methods.jl:3-45 */
 int to_solve_al(TOHandle h, const TOALOptions *o);       /* augmented_lagrangian_methods.jl:2-36 */
-int to_solve_altro(TOHandle h, const TOALTROOptions *o); /* altro_methods.jl:2-53 (projected Newton off) */
+int to_solve_altro(TOHandle h, const TOALTROOptions *o); /* altro_methods.jl:2-53 */
 /* Variant that does not wait for the END of the device work: the result copies of to_get_* and to_sync() wait.
  * It is not a pure enqueue: the lockstep engine replays its tick until the device-side list of live problems is
  * empty, so the host thread polls that (pinned) counter while the device works and returns once the last

@@ -57,6 +57,8 @@ struct TOALTROOptions
     R_inf::Float64
     dynamically_feasible_projection::Int32; resolve_feasible_problem::Int32
     R_minimum_time::Float64; dt_max::Float64; dt_min::Float64
+    projected_newton::Int32; pn_n_steps::Int32
+    projected_newton_tolerance::Float64; pn_feasibility_tolerance::Float64; pn_active_set_tolerance::Float64
 end
 struct TOResult
     J::Float64; c_max::Float64
@@ -193,9 +195,12 @@ c_opts(o::TO.AugmentedLagrangianSolverOptions) = TOALOptions(c_opts(o.opts_uncon
     o.gradient_norm_tolerance, o.gradient_norm_tolerance_intermediate, o.constraint_tolerance, o.iterations,
     o.kickout_max_penalty, o.dual_min, o.dual_max, o.penalty_max, o.penalty_initial, o.penalty_scaling)
 function c_opts(o::TO.ALTROSolverOptions)
-    o.projected_newton && error("TrajOptB200: projected Newton polish is not on the device path; set projected_newton=false")
+    pn = o.opts_pn
+    (!o.projected_newton || pn.solve_type == :feasible) ||
+        error("TrajOptB200: ProjectedNewtonSolverOptions.solve_type=$(pn.solve_type) is not on the device path (only :feasible)")
     TOALTROOptions(c_opts(o.opts_al), o.R_inf, o.dynamically_feasible_projection, o.resolve_feasible_problem,
-                   o.R_minimum_time, o.dt_max, o.dt_min)
+                   o.R_minimum_time, o.dt_max, o.dt_min, o.projected_newton, pn.n_steps,
+                   o.projected_newton_tolerance, pn.feasibility_tolerance, pn.active_set_tolerance)
 end
 
 # ---- the solver-like object returned to the caller (docs/src/solvers.md:27-51) -----------------------

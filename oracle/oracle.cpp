@@ -1120,6 +1120,8 @@ static bool al_solve(Ctx& c, const TOALOptions& o, ALStats& st) {
     return true;
 }
 
+#include "oracle_pn.hpp"
+
 // ------------------------------------------------------------------------------------------
 // building the (augmented) Spec from the public descriptor
 // ------------------------------------------------------------------------------------------
@@ -1269,11 +1271,17 @@ enum Mode { MODE_ILQR = 0, MODE_AL = 1, MODE_ALTRO = 2 };
 static void solve_one(const TOProblemDesc& D, int mode, const TOALTROOptions& ao, const double* x0, const double* U0,
                       const double* X0, bool want_trace, Out& out) {
     const int n0 = D.n, m0 = D.m, N = D.N;
-    const TOALOptions& alo = ao.opts_al;
+    TOALOptions alo = ao.opts_al;
     bool inf = false, mt = false;
+    const bool pn = (mode == MODE_ALTRO) && ao.projected_newton;
     if (mode == MODE_ALTRO) {
         inf = (X0 != nullptr);     // altro_methods.jl:102 (X[1] not all NaN)
         mt = (D.tf == 0.0);        // :111
+        if (pn) {                  // :6-14
+            if (ao.projected_newton_tolerance >= 0) alo.constraint_tolerance = ao.projected_newton_tolerance;
+            else { alo.constraint_tolerance = 0; alo.kickout_max_penalty = 1; }
+            if (mt) { std::fprintf(stderr, "oracle: projected Newton with minimum time is not supported (MinTimeCost has no hessian!)\n"); std::abort(); }
+        }
     }
     Spec S;
     build_spec(D, inf, mt, &ao, S);
@@ -1322,6 +1330,14 @@ static void solve_one(const TOProblemDesc& D, int mode, const TOALTROOptions& ao
     } else {
         used_al = true;
         ok = al_solve(c, alo, st);
+    }
+    // projected Newton on prob_altro (altro_methods.jl:31-39)
+    bool pn_done = false;
+    double pn_J = 0.0, pn_cmax = 0.0;
+    if (ok && pn) {
+        PNOpts po{ao.pn_n_steps, ao.pn_feasibility_tolerance, ao.pn_active_set_tolerance};
+        if (pn_solve(S, p, po, pn_J, pn_cmax)) pn_done = true;
+        else c.status |= TO_STATUS_PN_FAILED;
     }
     // process_results! (altro_methods.jl:56-95)
     if (ok && mode == MODE_ALTRO && inf) {
@@ -1377,6 +1393,7 @@ static void solve_one(const TOProblemDesc& D, int mode, const TOALTROOptions& ao
             for (int k = 0; k < N; k++) for (int i = 0; i < n0; i++) out.X[k][i] = p.X[k][i];
             for (int k = 0; k < N - 1; k++) for (int i = 0; i < m0; i++) out.U[k][i] = p.U[k][i];
             finish(c, used_al ? &st : nullptr, out);
+            if (pn_done) { out.res.J = pn_J; out.res.c_max = pn_cmax; }
             pack_duals(c, out);
         }
         out.dts.assign(N - 1, D.dt);
@@ -1389,6 +1406,7 @@ static void solve_one(const TOProblemDesc& D, int mode, const TOALTROOptions& ao
     out.dts.assign(N - 1, D.dt);
     if (mt) for (int k = 0; k < N - 1; k++) { double h = p.U[k][S.m - 1]; out.dts[k] = h * h; }
     finish(c, used_al ? &st : nullptr, out);
+    if (pn_done) { out.res.J = pn_J; out.res.c_max = pn_cmax; }
     pack_duals(c, out);
 }
 
@@ -1414,6 +1432,8 @@ void oracle_default_al_options(TOALOptions* o) {
 }
 void oracle_default_altro_options(TOALTROOptions* o) {
     oracle_default_al_options(&o->opts_al);
+    o->projected_newton = 0; o->pn_n_steps = 1; o->projected_newton_tolerance = 1e-3;
+    o->pn_feasibility_tolerance = 1e-6; o->pn_active_set_tolerance = 1e-3;
     o->R_inf = 1.0; o->dynamically_feasible_projection = 1; o->resolve_feasible_problem = 1;
     o->R_minimum_time = 1.0; o->dt_max = 1.0; o->dt_min = 1e-3;
 }

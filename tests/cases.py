@@ -138,6 +138,18 @@ def _quad_obs(B):
     return p, al, x0, None
 
 
+def _quad_maze(B):
+    """problems/quadrotor_maze.jl (44 cylinders, state + control bounds, terminal box) from the hover controls, with the AL options
+    of benchmark/quadrotor_benchmarks.jl:12-34 the maze benchmark shares with the line problem"""
+    p = problems.quadrotor_maze()
+    x0 = problems.batch_x0("quadrotor", B)
+    x0[0] = p.x0
+    o = problems.quadrotor_bench_options()
+    o.opts_al.iterations = 5  # from hover the straight line runs into the middle wall: keep the (diverging) solve short
+    o.opts_al.opts_uncon.iterations = 60
+    return p, o, x0, None
+
+
 def _pend_mintime(B):
     """test/minimum_time_tests.jl:17-19,38-46 (pendulum, R_minimum_time=15, dt_max=0.15)"""
     p = problems.pendulum()
@@ -204,6 +216,7 @@ CASES = {
     "park_inf_altro": _park_inf,
     "car_3obs_altro": _car_3obs,
     "quad_obs_al": _quad_obs,
+    "quad_maze_altro": _quad_maze,
     "pend_mintime": _pend_mintime,
     "pend_rk4_altro": _pend_integrator("rk4"),
     "pend_midpoint_altro": _pend_integrator("midpoint"),

@@ -28,8 +28,19 @@ def test_reference_options_outside_the_device_path_are_refused():
     for kw in (dict(bp_reg_type=":state"), dict(gradient_type=":feedforward"), dict(gradient_type="l2")):
         with pytest.raises(NotImplementedError, match="not on the device path"):
             to.iLQRSolverOptions(**kw).to_c()
-    with pytest.raises(NotImplementedError, match="projected Newton"):
-        to.ALTROSolverOptions(projected_newton=True).to_c()
+    with pytest.raises(NotImplementedError, match="solve_type"):
+        to.ALTROSolverOptions(projected_newton=True, opts_pn=to.ProjectedNewtonSolverOptions(solve_type=":optimal")).to_c()
+
+
+def test_projected_newton_options_reach_the_abi():
+    # altro_solver.jl:54-65 + direct_solvers.jl:14-30; the dead ALTRO fields are accepted and ignored
+    o = to.ALTROSolverOptions(projected_newton=True, projected_newton_tolerance=1e-4, constraint_tolerance_infeasible=1e-5,
+                              penalty_scaling_minimum_time_equality=2.0,
+                              opts_pn=to.ProjectedNewtonSolverOptions(feasibility_tolerance=1e-8, n_steps=2)).to_c()
+    assert (o.projected_newton, o.pn_n_steps, o.projected_newton_tolerance) == (1, 2, 1e-4)
+    assert (o.pn_feasibility_tolerance, o.pn_active_set_tolerance) == (1e-8, 1e-3)
+    d = to.ALTROSolverOptions().to_c()
+    assert (d.projected_newton, d.pn_n_steps, d.pn_feasibility_tolerance) == (0, 1, 1e-6)
 
 
 def test_options_nest_like_the_reference():

@@ -60,7 +60,9 @@ class TOALOptions(C.Structure):
 class TOALTROOptions(C.Structure):
     _fields_ = [("opts_al", TOALOptions), ("R_inf", C.c_double), ("dynamically_feasible_projection", C.c_int32),
                 ("resolve_feasible_problem", C.c_int32), ("R_minimum_time", C.c_double), ("dt_max", C.c_double),
-                ("dt_min", C.c_double)]
+                ("dt_min", C.c_double), ("projected_newton", C.c_int32), ("pn_n_steps", C.c_int32),
+                ("projected_newton_tolerance", C.c_double), ("pn_feasibility_tolerance", C.c_double),
+                ("pn_active_set_tolerance", C.c_double)]
 
 
 class TOResult(C.Structure):

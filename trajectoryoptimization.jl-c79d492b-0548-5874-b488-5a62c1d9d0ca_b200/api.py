@@ -343,15 +343,36 @@ class AugmentedLagrangianSolverOptions(_Opts):
         return o
 
 
+class ProjectedNewtonSolverOptions(_Opts):
+    """src/solvers/direct/direct_solvers.jl:14-30.  Only solve_type = :feasible is on the device path (the one ALTRO uses
+    in every reference benchmark and example)."""
+    _defaults = dict(n_steps=1, solve_type="feasible", active_set_tolerance=1e-3, feasibility_tolerance=1e-6)
+
+
 class ALTROSolverOptions(_Opts):
     _defaults = dict(opts_al=AugmentedLagrangianSolverOptions, R_inf=1.0, dynamically_feasible_projection=True,
                      resolve_feasible_problem=True, R_minimum_time=1.0, dt_max=1.0, dt_min=1e-3,
-                     projected_newton=False, projected_newton_tolerance=1e-3)
+                     projected_newton=False, opts_pn=ProjectedNewtonSolverOptions, projected_newton_tolerance=1e-3)
+    # declared at altro_solver.jl:15,27-52 and read nowhere in the reference (SURVEY Q6): accepted and ignored
+    _ignored = ("constraint_tolerance_infeasible", "penalty_initial_infeasible", "penalty_scaling_infeasible",
+                "penalty_initial_minimum_time_inequality", "penalty_initial_minimum_time_equality",
+                "penalty_scaling_minimum_time_inequality", "penalty_scaling_minimum_time_equality")
+
+    def __init__(self, **kw):
+        for k in self._ignored:
+            kw.pop(k, None)
+        super().__init__(**kw)
 
     def to_c(self):
-        if self.projected_newton:
-            raise NotImplementedError("projected Newton polish is out of scope (SURVEY §8f); set projected_newton=False")
         o = abi.TOALTROOptions()
+        o.projected_newton = int(bool(self.projected_newton))
+        pn = self.opts_pn
+        if self.projected_newton and str(pn.solve_type).lstrip(":") != "feasible":
+            raise NotImplementedError("ProjectedNewtonSolverOptions.solve_type=%r is not on the device path (only :feasible)" % (pn.solve_type,))
+        o.pn_n_steps = int(pn.n_steps)
+        o.projected_newton_tolerance = float(self.projected_newton_tolerance)
+        o.pn_feasibility_tolerance = float(pn.feasibility_tolerance)
+        o.pn_active_set_tolerance = float(pn.active_set_tolerance)
         o.opts_al = self.opts_al.to_c()
         o.R_inf = self.R_inf
         o.dynamically_feasible_projection = int(self.dynamically_feasible_projection)

@@ -53,6 +53,9 @@ struct Variant {
     double* cand_bulk = nullptr;   // bulk candidate trajectories: trial_group per problem
     double* res_scratch = nullptr; // resident kernel: cost scratch of res_slots CTAs
     unsigned int res_slots = 0;
+    double* pn_scratch = nullptr;  // projected Newton: block factors and vectors of pn_slots CTAs
+    int pn_slots = 0, pn_smem = 0;
+    unsigned long long pn_stride = 0;
 };
 
 }  // namespace
@@ -147,6 +150,9 @@ void free_variant(Variant& v) {
     if (v.cand_bulk) cudaFree(v.cand_bulk);
     if (v.res_scratch) cudaFree(v.res_scratch);
     v.res_scratch = nullptr;
+    if (v.pn_scratch) cudaFree(v.pn_scratch);
+    v.pn_scratch = nullptr;
+    v.pn_slots = 0;
     v.res_slots = 0;
     v.cand_bulk = nullptr;
     v.cand_alloc = nullptr;
@@ -638,11 +644,45 @@ int check_opts(TOSolver* s, const TOALOptions& o) {
     return 0;
 }
 
+// projected-Newton polish of every problem of the batch (altro_methods.jl:31-39), after the AL solve of variant `which`
+int launch_pn(TOSolver* s, int which, const TOALTROOptions& ao) {
+    Variant& v = s->var[which];
+    if (!v.pn_scratch) {
+        int slots = 0, smem = 0;
+        const int rc = v.ki->pn_setup(s->sm_count, s->d.N, v.P.nrows, &slots, &smem);
+        if (rc != 0 || slots < 1) return s->fail(TO_ERR_UNSUPPORTED, "projected Newton is not available for this problem variant (minimum time)");
+        slots = std::min(slots, s->B);
+        v.pn_stride = v.ki->pn_scratch_doubles(s->d.N, v.P.Ptot);
+        if (cudaMalloc(&v.pn_scratch, (size_t)slots * v.pn_stride * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            return s->fail(TO_ERR_NOMEM, "cudaMalloc failed (projected-Newton scratch)");
+        }
+        v.pn_slots = slots;
+        v.pn_smem = smem;
+    }
+    DevBatch Bt{};
+    Bt.B = s->B; Bt.n_out = s->d.n; Bt.m_out = s->d.m;
+    Bt.x0 = s->x0; Bt.X = s->X; Bt.U = s->U; Bt.dts = s->dts; Bt.res = s->res;
+    v.ki->pn_launch(v.pn_slots, v.pn_smem, s->stream, v.P, Bt, v.lc, ao.pn_n_steps, ao.pn_feasibility_tolerance, ao.pn_active_set_tolerance,
+                    v.pn_scratch, v.pn_stride);
+    CK_RET(s, cudaGetLastError());
+    s->launches += 1;
+    return 0;
+}
+
 int solve_common(TOSolver* s, int api_mode, const TOALTROOptions& ao, bool sync) {
     CK_RET(s, cudaSetDevice(s->device));
     int rc = check_opts(s, ao.opts_al);
     if (rc) return rc;
-    const TOALOptions& alo = ao.opts_al;
+    TOALOptions alo = ao.opts_al;
+    const bool pn = (api_mode == 2) && ao.projected_newton != 0;
+    if (pn) {  // altro_methods.jl:6-14
+        if (s->engine != 1) return s->fail(TO_ERR_UNSUPPORTED, "projected Newton runs on the lockstep engine only (unset TRAJOPT_B200_ENGINE)");
+        if (s->d.tf == 0.0) return s->fail(TO_ERR_UNSUPPORTED, "projected Newton with minimum time: MinTimeCost has no hessian! in the reference");
+        if (ao.pn_n_steps < 1) return s->fail(TO_ERR_INVALID, "pn_n_steps must be >= 1");
+        if (ao.projected_newton_tolerance >= 0) alo.constraint_tolerance = ao.projected_newton_tolerance;
+        else { alo.constraint_tolerance = 0; alo.kickout_max_penalty = 1; }
+    }
     s->launches = 0;
     s->ticks = 0;
     for (double& v : s->phase_ms) v = 0.0;
@@ -666,6 +706,7 @@ int solve_common(TOSolver* s, int api_mode, const TOALTROOptions& ao, bool sync)
         const int which = inf ? 1 : (mt ? 2 : 0);
         if ((rc = build_variant(s, which, &ao))) return rc;
         if ((rc = launch(s, which, 1, alo, true, false, false, X0_in, s->U0))) return rc;
+        if (pn && (rc = launch_pn(s, which, ao))) return rc;
         if (inf && ao.resolve_feasible_problem) {
             // infeasible_to_feasible_problem + projection! + second AL solve (altro_methods.jl:67-78)
             if ((rc = build_variant(s, 0, &ao))) return rc;
@@ -699,6 +740,8 @@ void to_default_altro_options(TOALTROOptions* o) {
     to_default_al_options(&o->opts_al);
     o->R_inf = 1.0; o->dynamically_feasible_projection = 1; o->resolve_feasible_problem = 1;
     o->R_minimum_time = 1.0; o->dt_max = 1.0; o->dt_min = 1e-3;
+    o->projected_newton = 0; o->pn_n_steps = 1; o->projected_newton_tolerance = 1e-3;
+    o->pn_feasibility_tolerance = 1e-6; o->pn_active_set_tolerance = 1e-3;
 }
 
 int to_device_count(void) {

@@ -129,6 +129,12 @@ struct KernelInfo {
     int (*ls_setup)(int sm_count, int N, int nrows, LsGrids* g);
     void (*ls_launch)(int phase, const LsGrids& g, cudaStream_t st, const DevProblem& P, const DevBatch& B, const DevCtl& c,
                       const LsCtl& lc, int cur, int grp);
+    // projected-Newton polish (pn.cuh): CTAs that can be resident (0 = not available for this variant) and their dynamic smem;
+    // scratch doubles per CTA; launch over the whole batch
+    int (*pn_setup)(int sm_count, int N, int nrows, int* slots, int* smem);
+    unsigned long long (*pn_scratch_doubles)(int N, int Ptot);
+    void (*pn_launch)(int grid, int smem, cudaStream_t st, const DevProblem& P, const DevBatch& B, const LsCtl& lc, int n_steps,
+                      double feas_tol, double act_tol, double* scratch, unsigned long long stride);
 };
 
 

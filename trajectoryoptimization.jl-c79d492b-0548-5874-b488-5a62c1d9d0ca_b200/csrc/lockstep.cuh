@@ -2437,6 +2437,7 @@ __global__ void __launch_bounds__(64) ls_accept_kernel(const DevProblem P, const
 
 }  // namespace tob
 #include "resident.cuh"
+#include "pn.cuh"
 namespace tob {
 
 // ------------------------------------------------------------------------------------------
@@ -2575,6 +2576,31 @@ template <class C> void ls_launch_fn(int phase, const LsGrids& g, cudaStream_t s
     }
 }
 
+template <class C> int ls_pn_setup_fn(int sm_count, int N, int nrows, int* slots, int* smem) {
+    *slots = 0;
+    *smem = 0;
+    if constexpr (C::MT || PnDims<C>::R > 64) {
+        return 0;  // MinTimeCost has no hessian! in the reference (projected_newton.jl:137-146 would throw): not available
+    } else {
+        const int bytes = (int)(((size_t)ls_tab_bytes(N, nrows) + 15) & ~(size_t)15) + (int)sizeof(PnSmem<C>);
+        if (cudaFuncSetAttribute(ls_pn_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) { cudaGetLastError(); return -1; }
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_pn_kernel<C>, LS_PN_THREADS, bytes);
+        if (nb < 1) return -2;
+        *slots = sm_count * nb;
+        *smem = bytes;
+        return 0;
+    }
+}
+template <class C> unsigned long long ls_pn_scratch_fn(int N, int Ptot) { return pn_layout<C>(N, Ptot).total; }
+template <class C> void ls_pn_launch_fn(int grid, int smem, cudaStream_t st, const DevProblem& P, const DevBatch& B, const LsCtl& lc, int n_steps,
+                                        double feas_tol, double act_tol, double* scratch, unsigned long long stride) {
+    if constexpr (!(C::MT || PnDims<C>::R > 64)) {
+        PnOptsDev po{n_steps, feas_tol, act_tol};
+        ls_pn_kernel<C><<<grid, LS_PN_THREADS, smem, st>>>(P, B, lc, po, scratch, stride);
+    }
+}
+
 template <class C> KernelInfo make_info() {
     KernelInfo k;
     k.model = C::MODEL; k.integ = C::INTEG; k.inf = C::INF; k.mt = C::MT; k.n = C::n; k.m = C::m;
@@ -2586,6 +2612,9 @@ template <class C> KernelInfo make_info() {
     k.ls_ws_doubles = ls_ws_doubles_fn<C>;
     k.ls_setup = ls_setup_fn<C>;
     k.ls_launch = ls_launch_fn<C>;
+    k.pn_setup = ls_pn_setup_fn<C>;
+    k.pn_scratch_doubles = ls_pn_scratch_fn<C>;
+    k.pn_launch = ls_pn_launch_fn<C>;
     return k;
 }
 

@@ -216,6 +216,73 @@ def quad_obs():
     return api.Problem(model, obj, constraints=cons, x0=x0, xf=xf, N=N, dt=dt)
 
 
+def maze_cylinders():
+    """problems/quadrotor_maze.jl:24-63: the 44 cylinders (x, y, radius) of the maze, in the file's order."""
+    r = 2.0
+    cyl = []
+    for i in np.linspace(-25.0, -10.0, 5):
+        cyl.append((float(i), 10.0, r))
+    for i in np.linspace(10.0, 25.0, 5):
+        cyl.append((float(i), 10.0, r))
+    for i in np.linspace(-5.0, 5.0, 4):
+        cyl.append((float(i), 30.0, r))
+    for i in np.linspace(-25.0, -10.0, 5):
+        cyl.append((float(i), 50.0, r))
+    for i in np.linspace(10.0, 25.0, 5):
+        cyl.append((float(i), 50.0, r))
+    for i in np.linspace(10.0 + 2 * r, 50.0 - 2 * r, 10):
+        cyl.append((-25.0, float(i), r))
+    for i in np.linspace(10.0 + 2 * r, 50.0 - 2 * r, 10):
+        cyl.append((25.0, float(i), r))
+    return cyl
+
+
+def quadrotor_maze(with_guess=False):
+    """problems/quadrotor_maze.jl: the quadrotor of problems/quadrotor.jl through a maze of 44 cylinders (circle rows with the
+    quadrotor radius added, :66-70), control bounds at k = 1, state + control bounds and the maze at 1 < k < N, terminal box.
+    `with_guess=True` also sets the state guess X0 (natural cubic spline through the 7 way points, :110-118), which makes ALTRO
+    add 13 slack controls (m = 17): wider than the 16-lane group of the backward pass, so the engine refuses that variant
+    loudly ("no sm_100a kernel instantiated"); without the guess it is an AL / ALTRO problem like quad_obs."""
+    model = api.rk3(api.Dynamics.quadrotor)
+    n, m, N, tf = 13, 4, 101, 5.0
+    dt = tf / (N - 1)
+    x0 = np.zeros(n)
+    x0[0:3] = [0.0, 0.0, 10.0]
+    x0[3] = 1.0
+    xf = np.zeros(n)
+    xf[0:3] = [0.0, 60.0, 10.0]
+    xf[3] = 1.0
+    Q = _eye(n, 1e-3)
+    Q[3:7, 3:7] = _eye(4, 1e-2)
+    obj = api.LQRObjective(Q, _eye(m, 1e-4), _eye(n, 1000.0), xf, N)
+    x_max, x_min = np.full(n, np.inf), np.full(n, -np.inf)
+    x_max[0:3] = [25.0, np.inf, 20.0]
+    x_min[0:3] = [-25.0, -np.inf, 0.0]
+    bnd1 = api.BoundConstraint(n, m, u_min=0.0, u_max=50.0)
+    bnd2 = api.BoundConstraint(n, m, u_min=0.0, u_max=50.0, x_min=x_min, x_max=x_max)
+    xU, xL = xf.copy(), xf.copy()
+    xU[3:7], xL[3:7] = np.inf, -np.inf
+    bnd_xf = api.BoundConstraint(n, m, x_min=xL, x_max=xU)
+    r_quad = 2.0
+    maze = api.CircleConstraints([(cx, cy, cr + r_quad) for cx, cy, cr in maze_cylinders()], "maze")
+    cons = api.Constraints(N)
+    cons.add(0, bnd1)
+    for k in range(1, N - 1):
+        cons.add(k, bnd2)
+        cons.add(k, maze)
+    cons.add(N - 1, bnd_xf)
+    X0 = None
+    if with_guess:
+        Xg = np.zeros((7, n))
+        Xg[:, 3] = 1.0
+        Xg[0], Xg[6] = x0, xf
+        Xg[1:6, 0] = [0.0, -12.5, -20.0, -12.5, 0.0]
+        Xg[1:6, 1] = [15.0, 20.0, 30.0, 40.0, 45.0]
+        Xg[1:6, 2] = 10.0
+        X0 = natural_spline_rows(N, tf, [list(r) for r in Xg])
+    return api.Problem(model, obj, constraints=cons, x0=x0, xf=xf, N=N, dt=dt, U0=np.full((N - 1, m), 0.5 * 9.81 / 4.0), X0=X0)
+
+
 def acrobot(N=151, dt=0.01, Qs=1e-2, Rs=1e-2, Qfs=100.0):
     """problems/acrobot.jl (goal constraint at N)."""
     model = api.rk3(api.Dynamics.acrobot_model)
