@@ -1198,18 +1198,30 @@ static void build_spec(const TOProblemDesc& D, bool inf, bool mt, const TOALTROO
         }
         // ALTRO transforms: non-bound rows first, bounds after (constraint_sets.jl:135-150)
         out = nonb;
+        // Both transforms in one solve (altro_methods.jl:98-124): minimum_time_problem runs on the slack problem, so the :infeasible
+        // rows come BEFORE the re-combined bound (minimum_time.jl:132-141), and combine(bnd, mt_bnd) appends the sqrt(dt) bounds
+        // after the ORIGINAL m0 controls of the knot's BoundConstraint (constraints.jl:195-203): they land on the first slack
+        // control.  A knot without a BoundConstraint gets bnd0 of the slack problem's size, whose extra entry is sqrt(dt) itself.
+        const bool both = inf && mt;
+        const int tau_col = (both && has_bound) ? nbar + m0 : nbar + S.m - 1;
+        if (both && !term) {
+            for (int i = 0; i < n0; i++) {
+                Row r; r.kind = R_LIN; r.eq = true; r.col = nbar + m0 + i; r.sign = 1.0; r.a = 0.0; r.b = r.c = r.r = 0;
+                out.push_back(r);
+            }
+        }
         if (mt) {
             // minimum_time.jl:126-147: combine(bnd, mt_bnd): [x_max; u_max; sqrt(dt_max); x_min; u_min; sqrt(dt_min)]
             out.insert(out.end(), bxmax.begin(), bxmax.end());
             if (!term) {
                 out.insert(out.end(), bumax.begin(), bumax.end());
-                Row r; r.kind = R_LIN; r.eq = false; r.col = nbar + S.m - 1; r.sign = 1.0; r.a = std::sqrt(ao->dt_max); r.b = r.c = r.r = 0;
+                Row r; r.kind = R_LIN; r.eq = false; r.col = tau_col; r.sign = 1.0; r.a = std::sqrt(ao->dt_max); r.b = r.c = r.r = 0;
                 out.push_back(r);
             }
             out.insert(out.end(), bxmin.begin(), bxmin.end());
             if (!term) {
                 out.insert(out.end(), bumin.begin(), bumin.end());
-                Row r; r.kind = R_LIN; r.eq = false; r.col = nbar + S.m - 1; r.sign = -1.0; r.a = std::sqrt(ao->dt_min); r.b = r.c = r.r = 0;
+                Row r; r.kind = R_LIN; r.eq = false; r.col = tau_col; r.sign = -1.0; r.a = std::sqrt(ao->dt_min); r.b = r.c = r.r = 0;
                 out.push_back(r);
             }
             (void)has_bound;
@@ -1219,7 +1231,7 @@ static void build_spec(const TOProblemDesc& D, bool inf, bool mt, const TOALTROO
             out.insert(out.end(), bxmin.begin(), bxmin.end());
             if (!term) out.insert(out.end(), bumin.begin(), bumin.end());
         }
-        if (inf && !term) {  // infeasible.jl:19-29 : + infeasible_constraints (constraints.jl:306-314)
+        if (inf && !both && !term) {  // infeasible.jl:19-29 : + infeasible_constraints (constraints.jl:306-314)
             for (int i = 0; i < n0; i++) {
                 Row r; r.kind = R_LIN; r.eq = true; r.col = nbar + m0 + i; r.sign = 1.0; r.a = 0.0; r.b = r.c = r.r = 0;
                 out.push_back(r);
@@ -1342,9 +1354,9 @@ static void solve_one(const TOProblemDesc& D, int mode, const TOALTROOptions& ao
     // process_results! (altro_methods.jl:56-95)
     if (ok && mode == MODE_ALTRO && inf) {
         // infeasible_to_feasible_problem (infeasible.jl:38-59): copy first n / m, projection! (Q9) = open-loop rollout
-        if (mt) { std::fprintf(stderr, "oracle: infeasible + minimum-time not supported\n"); std::abort(); }
+        // with minimum time the slack-free problem is the minimum-time problem again (infeasible.jl:43-51)
         Spec S0;
-        build_spec(D, false, false, &ao, S0);
+        build_spec(D, false, mt, &ao, S0);
         Ctx c2;
         c2.S = &S0;
         c2.tr = c.tr;
@@ -1352,19 +1364,25 @@ static void solve_one(const TOProblemDesc& D, int mode, const TOALTROOptions& ao
         c2.steps_total = c.steps_total;
         c2.p.S = &S0;
         c2.p.x0.assign(x0, x0 + n0);
-        c2.p.X.assign(N, vec(n0));
-        c2.p.U.assign(N - 1, vec(m0));
+        if (mt) c2.p.x0.push_back(0.0);
+        const int n2 = S0.n, m2 = S0.m;
+        c2.p.X.assign(N, vec(n2));
+        c2.p.U.assign(N - 1, vec(m2));
         for (int k = 0; k < N; k++) for (int i = 0; i < n0; i++) c2.p.X[k][i] = p.X[k][i];
         for (int k = 0; k < N - 1; k++) for (int i = 0; i < m0; i++) c2.p.U[k][i] = p.U[k][i];
+        if (mt) {  // sqrt(dt) of the first solve: controls, and the extra state of every knot but the first (infeasible.jl:46-50)
+            for (int k = 0; k < N - 1; k++) c2.p.U[k][m2 - 1] = p.U[k][S.m - 1];
+            for (int k = 0; k < N; k++) c2.p.X[k][n2 - 1] = (k == 0) ? 0.0 : p.X[k][S.n - 1];
+        }
         if (ao.dynamically_feasible_projection) {
             // projection! (ilqr_methods.jl:179-190): K = d = 0 -> Ū = U, X̄ = rollout from x0; abort leaves the tail of X̄ zero
-            std::vector<vec> Xb(N, vec(n0, 0.0));
+            std::vector<vec> Xb(N, vec(n2, 0.0));
             Xb[0] = c2.p.x0;
             for (int k = 1; k < N; k++) {
                 dyn_eval(S0, Xb[k].data(), Xb[k - 1].data(), c2.p.U[k - 1].data());
                 double mx = 0, mu = 0; bool bad = false;
-                for (int i = 0; i < n0; i++) { double a = std::fabs(Xb[k][i]); if (a != a) bad = true; mx = std::max(mx, a); }
-                for (int i = 0; i < m0; i++) { double a = std::fabs(c2.p.U[k - 1][i]); if (a != a) bad = true; mu = std::max(mu, a); }
+                for (int i = 0; i < n2; i++) { double a = std::fabs(Xb[k][i]); if (a != a) bad = true; mx = std::max(mx, a); }
+                for (int i = 0; i < m2; i++) { double a = std::fabs(c2.p.U[k - 1][i]); if (a != a) bad = true; mu = std::max(mu, a); }
                 if (bad || !(mx < alo.opts_uncon.max_state_value && mu < alo.opts_uncon.max_control_value)) break;
             }
             c2.p.X = Xb;
@@ -1382,9 +1400,15 @@ static void solve_one(const TOProblemDesc& D, int mode, const TOALTROOptions& ao
                 st = st2;
                 used_al = true;
             }
-            out.X = c2.p.X; out.U = c2.p.U;
+            out.X.assign(N, vec(n0));
+            out.U.assign(N - 1, vec(m0));
+            for (int k = 0; k < N; k++) for (int i = 0; i < n0; i++) out.X[k][i] = c2.p.X[k][i];
+            for (int k = 0; k < N - 1; k++) for (int i = 0; i < m0; i++) out.U[k][i] = c2.p.U[k][i];
+            out.dts.assign(N - 1, D.dt);
+            if (mt) for (int k = 0; k < N - 1; k++) { double h = c2.p.U[k][m2 - 1]; out.dts[k] = h * h; }
             finish(c2, used_al ? &st : nullptr, out);
             pack_duals(c2, out);
+            return;
         } else {
             // without the re-solve the projected copy is discarded (altro_methods.jl:67-78): the
             // caller keeps the first n states / m controls of the infeasible solution
@@ -1397,6 +1421,7 @@ static void solve_one(const TOProblemDesc& D, int mode, const TOALTROOptions& ao
             pack_duals(c, out);
         }
         out.dts.assign(N - 1, D.dt);
+        if (mt) for (int k = 0; k < N - 1; k++) { double h = p.U[k][S.m - 1]; out.dts[k] = h * h; }
         return;
     }
     out.X.assign(N, vec(n0));

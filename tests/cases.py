@@ -159,6 +159,23 @@ def _pend_mintime(B):
     return p, o, np.broadcast_to(p.x0, (B, 2)).copy() + 0.05 * problems.batch_x0("pendulum", B), None
 
 
+def _inf_mintime(resolve):
+    """infeasible start AND minimum time in ONE ALTRO solve (altro_methods.jl:98-124; the wish-list at test/runtests.jl:65-90 names
+    it as untested): parallel park with a straight-line state guess and tf = 0.  The reference composes the two transforms so
+    that the sqrt(dt) bounds of knots that own a BoundConstraint land on the first slack control (see build_variant / build_spec):
+    the solve runs into the penalty ceiling instead of converging -- reproduced, and bit-compared, as it is."""
+    def make(B):
+        p = problems.parallel_park(infeasible=True)
+        p.tf = 0.0
+        x0 = problems.batch_x0("parallel_park", B)
+        x0[0] = 0.0
+        X0 = np.stack([problems.line_trajectory(x0[b], p.xf, p.N) for b in range(B)])
+        al = api.AugmentedLagrangianSolverOptions(iterations=8, penalty_scaling=10.0, constraint_tolerance=1e-3)
+        o = api.ALTROSolverOptions(opts_al=al, R_minimum_time=10.0, dt_max=0.2, dt_min=1e-3, resolve_feasible_problem=resolve)
+        return p, o, x0, X0
+    return make
+
+
 def _sqrt_opts(**al_kw):
     il = api.iLQRSolverOptions(square_root=True)
     return api.AugmentedLagrangianSolverOptions(opts_uncon=il, **al_kw)
@@ -218,6 +235,8 @@ CASES = {
     "quad_obs_al": _quad_obs,
     "quad_maze_altro": _quad_maze,
     "pend_mintime": _pend_mintime,
+    "park_inf_mintime": _inf_mintime(False),
+    "park_inf_mintime_resolve": _inf_mintime(True),
     "pend_rk4_altro": _pend_integrator("rk4"),
     "pend_midpoint_altro": _pend_integrator("midpoint"),
     "pend_sqrt_altro": _pend_sqrt_altro,

@@ -23,7 +23,8 @@ INSTANCES = [
     # rk3: every model, plus the ALTRO transforms the problem zoo uses (infeasible start, minimum time)
     (0, 0, 0, 0, 3),
     (1, 0, 0, 0, 3), (1, 0, 0, 1, 4),
-    (2, 0, 0, 0, 5), (2, 0, 1, 0, 5), (2, 0, 0, 1, 6),
+    (2, 0, 0, 0, 5), (2, 0, 1, 0, 5), (2, 0, 0, 1, 6), (2, 0, 1, 1, 6),   # car: + infeasible start AND minimum time in one solve
+    (1, 0, 1, 0, 3), (1, 0, 1, 1, 4),
     (3, 0, 0, 0, 5),
     (4, 0, 0, 0, 2),
     (5, 0, 0, 0, 5), (5, 0, 0, 1, 6),
@@ -72,7 +73,7 @@ def generate():
     return files
 
 
-KERNEL_DEPS = ("engine.cuh", "lockstep.cuh", "resident.cuh", "sqrt_bp.cuh", "engine_host.h", "models.cuh", "../build.py", "../../include/trajopt_b200.h")
+KERNEL_DEPS = ("engine.cuh", "lockstep.cuh", "resident.cuh", "pn.cuh", "sqrt_bp.cuh", "engine_host.h", "models.cuh", "../build.py", "../../include/trajopt_b200.h")
 HOST_DEPS = ("engine_host.h", "../build.py", "../../include/trajopt_b200.h")
 
 

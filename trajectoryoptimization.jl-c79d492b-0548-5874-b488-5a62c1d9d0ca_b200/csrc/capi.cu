@@ -82,7 +82,8 @@ struct TOSolver {
     unsigned int* queue = nullptr;
     double* debug = nullptr;
     size_t debug_doubles = 0;
-    Variant var[3];  // 0 plain, 1 infeasible, 2 minimum time
+    Variant var[4];  // 0 plain, 1 infeasible, 2 minimum time, 3 infeasible + minimum time
+    double *tau = nullptr, *xtau = nullptr;  // sqrt(dt) controls / extra state handed from variant 3 to the minimum-time re-solve
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int launches = 0;
@@ -169,7 +170,7 @@ void free_variant(Variant& v) {
 // min time:   (non-bound rows, combined bound incl. sqrt(dt) bounds, :min_time_eq for 1<k<N)   minimum_time.jl:126-147
 int build_variant(TOSolver* s, int which, const TOALTROOptions* ao) {
     Variant& v = s->var[which];
-    const bool inf = (which == 1), mt = (which == 2);
+    const bool inf = (which == 1 || which == 3), mt = (which == 2 || which == 3);
     double key[6] = {inf ? ao->R_inf : 0.0, mt ? ao->R_minimum_time : 0.0, mt ? ao->dt_max : 0.0, mt ? ao->dt_min : 0.0, 0, 0};
     if (v.built && memcmp(key, v.key, sizeof key) == 0) return 0;
     free_variant(v);
@@ -246,17 +247,27 @@ int build_variant(TOSolver* s, int which, const TOALTROOptions* ao) {
                     r.kind = DR_LIN; r.eq = eq; r.col = col; r.sign = sign; r.a = a;
                     return r;
                 };
+                // Both transforms in one solve (altro_methods.jl:98-124): minimum_time_problem runs on the slack problem, so the
+                // :infeasible rows come BEFORE the re-combined bound (minimum_time.jl:132-141), and combine(bnd, mt_bnd) appends the
+                // sqrt(dt) bounds after the ORIGINAL m0 controls of a knot's BoundConstraint (constraints.jl:195-203, u[1:m0+1]):
+                // they land on the first slack control, not on sqrt(dt).  A knot without a BoundConstraint gets bnd0 of the slack
+                // problem's size and there the bounds do reach sqrt(dt) (minimum_time.jl:131-137).  Reproduced as written.
+                const bool both = inf && mt;
+                const bool knot_has_bound = !(bxmax.empty() && bumax.empty() && bxmin.empty() && bumin.empty());
+                const int tau_col = (both && knot_has_bound) ? nbar + m0 : nbar + mbar - 1;
+                if (both && !term)
+                    for (int i = 0; i < n0; i++) out.push_back(lin(nbar + m0 + i, 1.0, 0.0, 1));
                 out.insert(out.end(), bxmax.begin(), bxmax.end());
                 if (!term) {
                     out.insert(out.end(), bumax.begin(), bumax.end());
-                    if (mt) out.push_back(lin(nbar + mbar - 1, 1.0, std::sqrt(ao->dt_max), 0));
+                    if (mt) out.push_back(lin(tau_col, 1.0, std::sqrt(ao->dt_max), 0));
                 }
                 out.insert(out.end(), bxmin.begin(), bxmin.end());
                 if (!term) {
                     out.insert(out.end(), bumin.begin(), bumin.end());
-                    if (mt) out.push_back(lin(nbar + mbar - 1, -1.0, std::sqrt(ao->dt_min), 0));
+                    if (mt) out.push_back(lin(tau_col, -1.0, std::sqrt(ao->dt_min), 0));
                 }
-                if (inf && !term)
+                if (inf && !both && !term)
                     for (int i = 0; i < n0; i++) out.push_back(lin(nbar + m0 + i, 1.0, 0.0, 1));
                 if (mt && k > 0 && !term) {
                     DevRow r{};
@@ -596,9 +607,17 @@ int ensure_dual_buffers(TOSolver* s, int P) {
 
 // enqueue one kernel over the whole batch
 int launch(TOSolver* s, int which, int mode, const TOALOptions& alo, bool altro_init, bool projection_first, bool accumulate,
-           const double* X0_in, const double* U0_in) {
+           const double* X0_in, const double* U0_in, bool tau_export = false, bool tau_import = false) {
     Variant& v = s->var[which];
     DevBatch Bt{};
+    if (tau_export || tau_import) {
+        if (!s->tau) {
+            if (cudaMalloc(&s->tau, (size_t)s->B * (s->d.N - 1) * 8) != cudaSuccess || cudaMalloc(&s->xtau, (size_t)s->B * s->d.N * 8) != cudaSuccess)
+                return s->fail(TO_ERR_NOMEM, "cudaMalloc failed (sqrt(dt) hand-over buffers)");
+        }
+        if (tau_export) { Bt.tau_out = s->tau; Bt.xtau_out = s->xtau; }
+        if (tau_import) { Bt.tau_in = s->tau; Bt.xtau_in = s->xtau; }
+    }
     Bt.B = s->B; Bt.n_out = s->d.n; Bt.m_out = s->d.m;
     Bt.x0 = s->x0; Bt.U0 = U0_in; Bt.X0 = X0_in;
     Bt.X = s->X; Bt.U = s->U; Bt.dts = s->dts; Bt.res = s->res;
@@ -702,15 +721,16 @@ int solve_common(TOSolver* s, int api_mode, const TOALTROOptions& ao, bool sync)
     } else {
         const bool inf = s->has_X0;          // altro_methods.jl:102
         const bool mt = (s->d.tf == 0.0);    // altro_methods.jl:111
-        if (inf && mt) return s->fail(TO_ERR_UNSUPPORTED, "infeasible start combined with minimum time is not supported yet");
-        const int which = inf ? 1 : (mt ? 2 : 0);
+        const int which = inf ? (mt ? 3 : 1) : (mt ? 2 : 0);
         if ((rc = build_variant(s, which, &ao))) return rc;
-        if ((rc = launch(s, which, 1, alo, true, false, false, X0_in, s->U0))) return rc;
+        if ((rc = launch(s, which, 1, alo, true, false, false, X0_in, s->U0, inf && mt, false))) return rc;
         if (pn && (rc = launch_pn(s, which, ao))) return rc;
         if (inf && ao.resolve_feasible_problem) {
-            // infeasible_to_feasible_problem + projection! + second AL solve (altro_methods.jl:67-78)
-            if ((rc = build_variant(s, 0, &ao))) return rc;
-            if ((rc = launch(s, 0, con ? 1 : 0, alo, false, ao.dynamically_feasible_projection != 0, true, s->X, s->U))) return rc;
+            // infeasible_to_feasible_problem + projection! + second AL solve (altro_methods.jl:67-78); with minimum time the
+            // slack-free problem is the minimum-time problem again, started from the sqrt(dt) of the first solve (infeasible.jl:43-51)
+            const int second = mt ? 2 : 0;
+            if ((rc = build_variant(s, second, &ao))) return rc;
+            if ((rc = launch(s, second, (con || mt) ? 1 : 0, alo, false, ao.dynamically_feasible_projection != 0, true, s->X, s->U, false, mt))) return rc;
         }
     }
     CK_RET(s, cudaEventRecord(s->ev1, s->stream));
@@ -822,7 +842,7 @@ void to_destroy(TOHandle s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto& v : s->var) free_variant(v);
     void* ptrs[] = {s->x0, s->U0, s->X0, s->X, s->U, s->dts, s->res, s->inner, s->outer, s->n_inner, s->n_outer,
-                    s->lam_out, s->mu_out, s->act_out, s->queue, s->debug};
+                    s->lam_out, s->mu_out, s->act_out, s->queue, s->debug, s->tau, s->xtau};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->h_counts) cudaFreeHost(s->h_counts);
     for (auto& e : s->ring_ev) if (e) cudaEventDestroy(e);
@@ -1052,7 +1072,7 @@ int to_debug_read(TOHandle s, double* out, int32_t doubles) {
     return 0;
 }
 int to_debug_grid(TOHandle s, int which, int32_t* grid, int32_t* smem, uint64_t* ws_doubles) {
-    if (!s || which < 0 || which > 2 || !s->var[which].built) return TO_ERR_INVALID;
+    if (!s || which < 0 || which > 3 || !s->var[which].built) return TO_ERR_INVALID;
     if (s->engine == 1) {
         *grid = s->var[which].grids.bp;
         *smem = s->var[which].grids.bp_smem;

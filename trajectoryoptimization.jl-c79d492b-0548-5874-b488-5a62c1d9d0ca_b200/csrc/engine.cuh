@@ -1288,6 +1288,12 @@ struct Solver {
             else if (C::MT && i == m - 1) v = sdt;  // minimum_time.jl:34
             ws[L.U + e] = v;
         }
+        if constexpr (C::MT) {
+            if (Bt.tau_in) {  // infeasible_to_feasible_problem with minimum time (infeasible.jl:43-51): sqrt(dt) of the previous solve
+                for (int k = lane; k < N - 1; k += 32) ws[L.U + (size_t)k * m + (m - 1)] = Bt.tau_in[(size_t)b * (N - 1) + k];
+                for (int k = lane; k < N; k += 32) ws[L.X + (size_t)k * n + (n - 1)] = (k == 0) ? 0.0 : Bt.xtau_in[(size_t)b * N + k];
+            }
+        }
         __syncwarp();
         if (C::INF && ctl.altro_init) {
             // slack_controls (infeasible.jl:62-80): u_s[k] = X0[k+1] - f(x̂[k],u[k]) on the original model
@@ -1345,6 +1351,12 @@ struct Solver {
                     if (C::MT) { const double h = U(k)[m - 1]; dtk = h * h; }
                     Bt.dts[(size_t)b * (N - 1) + k] = dtk;
                 }
+            if constexpr (C::MT) {
+                if (Bt.tau_out) {
+                    for (int k = lane; k < N - 1; k += 32) Bt.tau_out[(size_t)b * (N - 1) + k] = U(k)[m - 1];
+                    for (int k = lane; k < N; k += 32) Bt.xtau_out[(size_t)b * N + k] = X(k)[n - 1];
+                }
+            }
         }
         if (al_on && Bt.lam_out) {
             for (int e = lane; e < P.Ptot; e += 32) {

@@ -48,6 +48,11 @@ struct DevBatch {
     int outer_cap;
     double *lam_out, *mu_out;
     uint8_t* act_out;
+    // infeasible start + minimum time in one ALTRO solve (altro_methods.jl:98-124): the first solve exports sqrt(dt) of every knot
+    // (controls, [B][N-1]) and the extra state ([B][N]); the slack-free minimum-time re-solve starts from them
+    // (infeasible.jl:43-51).  Null otherwise.
+    double *tau_out, *xtau_out;
+    const double *tau_in, *xtau_in;
 };
 
 struct DevCtl {
