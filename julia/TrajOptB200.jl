@@ -281,6 +281,38 @@ end
 TO.solve!(prob::TO.Problem, b::B200) = solve_batch!([prob], b.opts, b.device)[1]
 TO.solve!(probs::Vector{<:TO.Problem}, b::B200) = solve_batch!(probs, b.opts, b.device)
 
+# the copying variants (src/solvers.jl:104-108): the caller's problem stays untouched, `(prob_solved, solver)` comes back
+function TO.solve(prob::TO.Problem, b::B200)
+    p = copy(prob)
+    solver = TO.solve!(p, b)
+    return p, solver
+end
+function TO.solve(probs::Vector{<:TO.Problem}, b::B200)
+    ps = [copy(p) for p in probs]
+    solvers = TO.solve!(ps, b)
+    return ps, solvers
+end
+
+"""
+    print_log(solver; io=stderr)
+
+The OuterLoop table of the reference's SolverLogger (src/logger.jl:10-38; columns iter / total / c_max as
+augmented_lagrangian_methods.jl:93-96 logs them), rebuilt from the histories the engine returned.
+"""
+function print_log(solver::B200Solver; io::IO=stderr)
+    st = solver.stats
+    haskey(st, :c_max) || return
+    logger = TO.SolverLogger(TO.OuterLoop, io=io)
+    TO.add_level!(logger, TO.OuterLoop, [:iter, :total, :c_max, :info], [6, 7, 12, 50], print_color=:yellow, indent=0)
+    total = 0
+    for i = 1:length(st[:c_max])
+        total += st[:iterations_inner][i]
+        d = logger[TO.OuterLoop].data
+        d[:iter] = i; d[:total] = total; d[:c_max] = st[:c_max][i]
+        println(logger, TO.OuterLoop)
+    end
+end
+
 "Route the package's own entry points to the GPU (drop-in): `solve!(prob, ALTROSolverOptions{Float64}())` etc."
 function enable!(; device::Int=0)
     @eval TO.solve!(prob::TO.Problem, opts::TO.ALTROSolverOptions) = TrajOptB200.solve_batch!([prob], opts, $device)[1]

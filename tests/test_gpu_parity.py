@@ -182,6 +182,25 @@ def test_readme_block_move(to):
     assert solver.stats["iterations"] == len(solver.stats["cost"]) == len(solver.stats["c_max"])
 
 
+def test_copying_solve_and_logger_tables(to):
+    """solve(prob, opts) (src/solvers.jl:104-108) leaves the caller's problem alone; the verbose tables of src/logger.jl are
+    rebuilt from the histories (one OuterLoop row per recorded outer iteration, one InnerLoop row per inner record)."""
+    prob = to.problems.doubleintegrator()
+    U_before, X_before = prob.U.copy(), prob.X.copy()
+    solved, solver = to.solve(prob, to.ALTROSolverOptions())
+    assert np.array_equal(prob.U, U_before) and np.array_equal(np.isnan(prob.X), np.isnan(X_before))
+    ref = to.problems.doubleintegrator()
+    to.solve_b(ref, to.ALTROSolverOptions())
+    assert np.array_equal(solved.X, ref.X) and np.array_equal(solved.U, ref.U)
+    log = to.format_log(solver)
+    rows = [ln for ln in log.splitlines() if ln[:1].isdigit()]
+    assert len(rows) == len(solver.stats["c_max"]) and "c_max" in log and "expected" in log
+    inner_rows = [ln for ln in log.splitlines() if ln.startswith("    ") and ln.strip()[:1].isdigit()]
+    assert len(inner_rows) == len(solver.inner)
+    both, solvers = to.solve([prob, prob], to.ALTROSolverOptions())
+    assert np.array_equal(both[0].X, solved.X) and np.array_equal(both[1].U, solved.U) and len(solvers) == 2
+
+
 def test_reference_integration_inequalities(to):
     """The reference's own solve-level tests, re-expressed as batch-of-1 solves:
     test/quadrotor_tests.jl:1-60 (rk4; iLQR reaches xf; AL with goal; AL with goal + control bounds),

@@ -49,3 +49,13 @@ def test_options_nest_like_the_reference():
     c = to.ALTROSolverOptions(opts_al=al, R_inf=0.5).to_c()
     assert c.opts_al.opts_uncon.iterations == 50 and c.opts_al.opts_uncon.square_root == 1
     assert c.opts_al.iterations == 7 and c.R_inf == 0.5
+
+
+def test_trim_entry_follows_the_reference_logger():
+    # src/logger.jl:171-194: fixed notation inside the column's range, exponent notation outside, a leading space for positives
+    from trajopt_b200.api import _trim_entry
+    assert _trim_entry(4458.9547984, 14) == " 4458.9547984 ".ljust(14)
+    assert _trim_entry(0.125, 10) == " 0.125".ljust(10)
+    assert _trim_entry(-3.5, 10) == "-3.5".ljust(10)
+    assert _trim_entry(1.0e-9, 10).strip() == "1e-09" and _trim_entry(12, 6) == "12".ljust(6)
+    assert _trim_entry(float("inf"), 10).strip() == "Inf"

@@ -13,7 +13,10 @@ reference's names and argument meaning (README.md:29-67):
     Problem, initial_controls_b   src/problem.jl:37-157      (`!` spelled `_b`)
     iLQRSolverOptions, AugmentedLagrangianSolverOptions, ALTROSolverOptions
     solve_b(prob, opts)           src/solvers.jl:91-94, altro_methods.jl:2-53
+    solve(prob, opts)             src/solvers.jl:104-108 (copying variant)
     solve_b([prob...], opts)      NEW: batched solve over B same-shape problems
+    format_log(solver)            src/logger.jl: the verbose InnerLoop / OuterLoop tables, from the returned histories
+    ProjectedNewtonSolverOptions  src/solvers/direct/direct_solvers.jl:14-30 (solve_type = :feasible)
 
 `solve_b` marshals the Problem into the POD descriptor of include/trajopt_b200.h and calls the CUDA
 engine.  There is no CPU path here: without the built extension or without a GPU it raises.
@@ -632,6 +635,75 @@ def solve_b(prob, opts, device=0, trace=True):
         return out if isinstance(prob, (list, tuple)) else out[0]
     finally:
         bs.close()
+
+
+def solve(prob, opts, device=0, trace=True):
+    """solve(prob, opts) (src/solvers.jl:104-108): the copying variant -- the caller's problem(s) stay untouched, the solved
+    copies are returned with the solver-like object(s): `(prob_solved, solver)`, or two lists for a batch."""
+    if isinstance(prob, (list, tuple)):
+        copies = [p.copy() for p in prob]
+        return copies, solve_b(copies, opts, device, trace)
+    cp = prob.copy()
+    return cp, solve_b(cp, opts, device, trace)
+
+
+# ------------------------------------------------------------------------------------------
+# SolverLogger tables (src/logger.jl) rebuilt from the returned histories
+# ------------------------------------------------------------------------------------------
+def _trim_entry(v, width):
+    """trim_entry (src/logger.jl:171-214): a value within `width` characters, fixed or exponent notation as the reference picks"""
+    if isinstance(v, (int, np.integer)):
+        return str(int(v)).ljust(width)
+    v = float(v)
+    if not math.isfinite(v):
+        return ("NaN" if v != v else ("Inf" if v > 0 else "-Inf")).ljust(width)
+    base = math.log10(abs(v)) if v != 0.0 else -math.inf
+    if -math.ceil(width / 2) + 1 < base < math.floor(width / 2):
+        prec = width - math.ceil(base) - 3 if base > 0 else width - 4
+        if prec <= 0:
+            width = width - prec + 1
+            prec = 1
+        txt = ("%.*f" % (int(prec), v)).rstrip("0").rstrip(".")
+    else:
+        w = 10 if width <= 8 else width
+        mant, ex = ("%.*e" % (max(0, w - 8), v)).split("e")
+        if "." in mant:
+            mant = mant.rstrip("0").rstrip(".")
+        txt = "%se%s%02d" % (mant, ex[0], abs(int(ex)))
+    if v >= 0:
+        txt = " " + txt  # positivespace=true
+    return txt.ljust(width)
+
+
+def _table(cols, widths, rows, indent):
+    head = " " * indent + "".join(c.ljust(w) for c, w in zip(cols, widths)) + "\n" + "_" * indent + "-" * sum(widths)
+    return "\n".join([head] + [" " * indent + "".join(_trim_entry(v, w) for v, w in zip(r, widths)) for r in rows])
+
+
+def format_log(solver):
+    """The verbose tables of the reference's SolverLogger (src/logger.jl:10-38,155-168): one InnerLoop table per inner solve
+    (iter cost expected z α ρ dJ grad, the columns record_iteration! and forwardpass! log, ilqr_methods.jl:84-88,
+    forward_pass.jl:75-78) followed by its OuterLoop row (iter total c_max, augmented_lagrangian_methods.jl:93-96).
+    Needs the histories (`trace=True`)."""
+    inner, stats = solver.inner, solver.stats
+    out = []
+    icols, iw = ["iter", "cost", "expected", "z", "α", "ρ", "dJ", "grad"], [5, 14, 12, 10, 10, 10, 10, 10]
+    ocols, ow = ["iter", "total", "c_max"], [6, 7, 12]
+    n_outer = len(stats.get("c_max", [])) if stats.get("iterations_inner") else 0
+    total = 0
+    for o in range(max(1, n_outer)):
+        rows = []
+        if inner is not None and len(inner):
+            sel = inner[inner["outer"] == max(0, o - 1)] if n_outer else inner
+            if n_outer and o == 0:
+                sel = sel[:0]  # the first outer record is taken before any inner solve
+            rows = [(int(r["iter"]), r["cost"], r["expected"], r["z"], r["alpha"], r["rho"], r["dJ"], r["gradient"]) for r in sel]
+        if rows:
+            out.append(_table(icols, iw, rows, 4))
+        if n_outer:
+            total += int(stats["iterations_inner"][o])
+            out.append(_table(ocols, ow, [(o + 1, total, stats["c_max"][o])], 0))
+    return "\n".join(out)
 
 
 def max_violation(prob):
