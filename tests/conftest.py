@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: BASELINE.json batch sizes (minutes on the GPU box); deselect with -m 'gpu and not slow'")
 
 
 @pytest.fixture(scope="session")
