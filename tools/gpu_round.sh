@@ -35,6 +35,7 @@ for step in "$@"; do
             echo "ncu resident exit $?" ;;
     resprof) for c in quad_altro escape_notebook cart_altro; do timeout 300 python tools/resident_profile.py $c 8; done > $OUT/${TAG}_resident_profile.log 2>&1
             echo "resprof exit $?"; cat $OUT/${TAG}_resident_profile.log ;;
+    ncu_resprof=*) RCASE="${step#ncu_resprof=}"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:ls_resident_kernel -c 1 -f -o $OUT/${TAG}_prof_resident python tools/resident_profile.py $RCASE 8 > $OUT/${TAG}_ncu_resident.log 2>&1; echo "ncu resident ($RCASE) exit $?" ;;
     ncu_resprof)
             timeout 900 ncu --set full --clock-control none --import-source on -k regex:'ls_resident_kernel' -c 1 -f -o $OUT/${TAG}_prof_resident \
                 python tools/resident_profile.py quad_altro 8 > $OUT/${TAG}_ncu_resident.log 2>&1

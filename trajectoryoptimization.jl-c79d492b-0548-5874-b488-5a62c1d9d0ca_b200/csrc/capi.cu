@@ -362,10 +362,19 @@ int ensure_engine_buffers(TOSolver* s, Variant& v) {
     }
     // tail mode keeps all 32 candidate trajectories of up to `cand_slots` live problems
     {
-        unsigned int slots = (unsigned int)s->sm_count * 8u;
+        // 32 resident problem-warps per SM: below that a tick is latency-bound and one launch with all step sizes beats up to three
+        // launches of 8 (measured, profiles/r02m: car_escape 16,384 problems 14.3 / 13.4 / 12.5 s at 8 / 16 / 32 per SM; the
+        // quadrotor is indifferent) -- as long as the candidates fit in a sixteenth of the free device memory
+        unsigned int slots = (unsigned int)s->sm_count * 32u;
+        const size_t per = (size_t)(N * v.ki->n + (N - 1) * v.ki->m) * 32;  // doubles per problem for 32 candidates (cand_span)
+        {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            const size_t fit = (free_b / 16) / (per * sizeof(double));
+            if ((size_t)slots > fit) slots = (unsigned int)std::max<size_t>(fit, (size_t)s->sm_count * 2);
+        }
         if (const char* env = getenv("TRAJOPT_B200_TAIL_THRESHOLD")) slots = (unsigned int)atoi(env);  // 0 disables tail mode
         if (slots > (unsigned int)s->B) slots = (unsigned int)s->B;
-        const size_t per = (size_t)(N * v.ki->n + (N - 1) * v.ki->m) * 32;  // doubles per problem for 32 candidates (cand_span)
         if (slots > 0 && cudaMalloc(&v.cand_alloc, (size_t)slots * per * sizeof(double)) == cudaSuccess) v.cand_slots = slots;
         else { cudaGetLastError(); v.cand_alloc = nullptr; v.cand_slots = 0; }
         // bulk: the G candidates of every problem (skipped if it would not leave a quarter of the device memory free)
@@ -384,7 +393,9 @@ int ensure_engine_buffers(TOSolver* s, Variant& v) {
         unsigned int slots = std::min<unsigned int>((unsigned int)std::max(0, v.grids.res_capacity), v.cand_slots);
         if (const char* env = getenv("TRAJOPT_B200_RESIDENT_THRESHOLD")) slots = std::min<unsigned int>(slots, (unsigned int)atoi(env));  // 0 disables
         const size_t per = 2 * (size_t)N * 32;  // res_scratch_doubles(N)
-        if (slots > 0 && cudaMalloc(&v.res_scratch, (size_t)slots * per * sizeof(double)) == cudaSuccess) v.res_slots = slots;
+        // scratch for up to 4 launch waves of CTAs (a CTA beyond the resident capacity starts when an earlier one ends)
+        const size_t scratch_slots = std::min<size_t>((size_t)slots * 4, (size_t)v.cand_slots);
+        if (slots > 0 && cudaMalloc(&v.res_scratch, scratch_slots * per * sizeof(double)) == cudaSuccess) v.res_slots = slots;
         else { cudaGetLastError(); v.res_scratch = nullptr; v.res_slots = 0; }
         v.lc.res_scratch = v.res_scratch;
     }
@@ -480,7 +491,19 @@ int run_lockstep_impl(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl&
         cudaEventRecord(e, st);
         tick_ev.push_back(e);
     };
-    const unsigned int res_threshold = (!c.o.opts_uncon.square_root && ntrial <= 32 && v.cand_alloc) ? v.res_slots : 0u;
+    // the resident kernel takes over when the live problems fit its CTAs twice over: a CTA then serves two problems one after
+    // the other, and nearly all of them end within a few iterations (the handful of stragglers sets the kernel's duration anyway)
+    // (measured, profiles/r02l: car_escape 16,384 problems 17.2 -> 14.3 s with two waves -- its lockstep tick costs 8 ms while a
+    // resident iteration costs 1 ms; the quadrotor's tail tick and resident iteration cost the same 0.65 ms, and two problems per
+    // CTA only serialise them: 7.40 -> 7.58 s.  So: two waves for problems with large per-knot constraint sets, one otherwise.)
+    int max_rows = 0;
+    for (int k = 0; k < s->d.N; k++) {
+        const int cls = (s->d.n_classes > 0) ? s->class_of_knot[k] : -1;
+        if (cls >= 0) max_rows = std::max(max_rows, (int)(s->class_row_start[cls + 1] - s->class_row_start[cls]));
+    }
+    unsigned int res_waves = (max_rows > 32) ? 2u : 1u;
+    if (const char* env = getenv("TRAJOPT_B200_RESIDENT_WAVES")) res_waves = (unsigned int)std::max(1, std::min(4, atoi(env)));
+    const unsigned int res_threshold = (!c.o.opts_uncon.square_root && ntrial <= 32 && v.cand_alloc) ? std::min(v.res_slots * res_waves, v.cand_slots) : 0u;
     for (long long t = 0; t < max_ticks; t++) {
         const int cur = (int)(t & 1);
         if (known_active <= res_threshold) {

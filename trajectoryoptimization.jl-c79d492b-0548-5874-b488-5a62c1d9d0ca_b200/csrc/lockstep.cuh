@@ -619,63 +619,95 @@ struct BpGroup {
                 const double z = xs[n + j];
                 own(sl.x, z, duu, au); own(sl.y, z, duu, au); own(sl.z, z, duu, au); own(sl.w, z, duu, au);
             }
-        } else
-        for (int r_ = 0; r_ < rc; r_++) {
-            const DevRow r = P.rows[rb + r_];
-            if (r.kind == DR_LIN) {
-                const int col = r.col;
-                const bool ownx = (j < n) && (col == j);
-                const bool ownu = !term && (j < m) && (col == n + j);
-                if (ownx || ownu) {
-                    const double z = xs[col];
-                    const double c = (r.sign > 0) ? (z - r.a) : (r.a - z);
-                    const double lam_r = lams[r_];
-                    const bool act = r.eq ? true : ((c >= 0.0) || (lam_r > 0.0));
-                    const double im = act ? mus[r_] : 0.0;
-                    const double g = im * c + lam_r;
-                    const double gj = (r.sign > 0) ? 1.0 : -1.0;
-                    if (ownx) { dxx = fma(gj * im, gj, dxx); ax = fma(gj, g, ax); }
-                    else { duu = fma(gj * im, gj, duu); au = fma(gj, g, au); }
-                }
-            } else {
-                const double gx = (j < n) ? row_jac_s(r, xs, j) : 0.0;
-                const double gu = (!term && j < m) ? row_jac_s(r, xs, n + j) : 0.0;
-                if (gx != 0.0 || gu != 0.0) {
-                    const double c = row_value_s(r, xs);
-                    const double lam_r = lams[r_];
-                    const bool act = r.eq ? true : ((c >= 0.0) || (lam_r > 0.0));
-                    const double im = act ? mus[r_] : 0.0;
-                    const double g = im * c + lam_r;
-                    if (gx != 0.0) {
-#pragma unroll
-                        for (int i = 0; i < n; i++) {
-                            const double gi = row_jac_s(r, xs, i);
-                            if (gi != 0.0) {
-                                if (i == j) dxx = fma(gi * im, gx, dxx);
-                                else Qxxc[i] = fma(gi * im, gx, Qxxc[i]);
+        } else {
+            auto row_body = [&](const int r_) {
+                const DevRow r = P.rows[rb + r_];
+                if (r.kind == DR_LIN) {
+                    const int col = r.col;
+                    const bool ownx = (j < n) && (col == j);
+                    const bool ownu = !term && (j < m) && (col == n + j);
+                    if (ownx || ownu) {
+                        const double z = xs[col];
+                        const double c = (r.sign > 0) ? (z - r.a) : (r.a - z);
+                        const double lam_r = lams[r_];
+                        const bool act = r.eq ? true : ((c >= 0.0) || (lam_r > 0.0));
+                        const double im = act ? mus[r_] : 0.0;
+                        const double g = im * c + lam_r;
+                        const double gj = (r.sign > 0) ? 1.0 : -1.0;
+                        if (ownx) { dxx = fma(gj * im, gj, dxx); ax = fma(gj, g, ax); }
+                        else { duu = fma(gj * im, gj, duu); au = fma(gj, g, au); }
+                    }
+                } else {
+                    const double gx = (j < n) ? row_jac_s(r, xs, j) : 0.0;
+                    const double gu = (!term && j < m) ? row_jac_s(r, xs, n + j) : 0.0;
+                    if (gx != 0.0 || gu != 0.0) {
+                        const double c = row_value_s(r, xs);
+                        const double lam_r = lams[r_];
+                        const bool act = r.eq ? true : ((c >= 0.0) || (lam_r > 0.0));
+                        const double im = act ? mus[r_] : 0.0;
+                        const double g = im * c + lam_r;
+                        if (gx != 0.0) {
+    #pragma unroll
+                            for (int i = 0; i < n; i++) {
+                                const double gi = row_jac_s(r, xs, i);
+                                if (gi != 0.0) {
+                                    if (i == j) dxx = fma(gi * im, gx, dxx);
+                                    else Qxxc[i] = fma(gi * im, gx, Qxxc[i]);
+                                }
                             }
+                            if (!term) {
+    #pragma unroll
+                                for (int i = 0; i < m; i++) {
+                                    const double gi = row_jac_s(r, xs, n + i);
+                                    if (gi != 0.0) Quxc[i] = fma(gi * im, gx, Quxc[i]);
+                                }
+                            }
+                            ax = fma(gx, g, ax);
                         }
-                        if (!term) {
-#pragma unroll
+                        if (gu != 0.0) {
+    #pragma unroll
                             for (int i = 0; i < m; i++) {
                                 const double gi = row_jac_s(r, xs, n + i);
-                                if (gi != 0.0) Quxc[i] = fma(gi * im, gx, Quxc[i]);
+                                if (gi != 0.0) {
+                                    if (i == j) duu = fma(gi * im, gu, duu);
+                                    else Quuc[i] = fma(gi * im, gu, Quuc[i]);
+                                }
                             }
+                            au = fma(gu, g, au);
                         }
-                        ax = fma(gx, g, ax);
-                    }
-                    if (gu != 0.0) {
-#pragma unroll
-                        for (int i = 0; i < m; i++) {
-                            const double gi = row_jac_s(r, xs, n + i);
-                            if (gi != 0.0) {
-                                if (i == j) duu = fma(gi * im, gu, duu);
-                                else Quuc[i] = fma(gi * im, gu, Quuc[i]);
-                            }
-                        }
-                        au = fma(gu, g, au);
                     }
                 }
+            };
+            if (rc > LAMCAP) {
+                // Large sets (car_escape: 170 circles per knot, most of them far away): a row that is inactive with a zero
+                // multiplier and a finite value contributes im = 0, g = +0, i.e. only +-0 terms to sums that are never -0 -- an exact
+                // no-op.  So the lanes first evaluate the rows in PARALLEL (one row per lane and round), and only the rows that do
+                // contribute are walked in row order by the sequential body (the same sums, bit for bit).
+                const int gshift = __ffs(gmask) - 1;
+                for (int base = 0; base < rc; base += GS) {
+                    const int rr = base + j;
+                    bool contrib = false;
+                    if (rr < rc) {
+                        const DevRow* r = &P.rows[rb + rr];
+                        const int kind = r->kind;
+                        if (kind == DR_LIN && term && r->col >= n) {
+                            contrib = false;  // a control row at the terminal knot: the body ignores it
+                        } else {
+                            const double c = row_value_s(*r, xs);
+                            const double lam_r = lams[rr];
+                            const bool act = r->eq ? true : ((c >= 0.0) || (lam_r > 0.0));
+                            contrib = act || !(lam_r == 0.0) || !isfinite(c);
+                        }
+                    }
+                    unsigned bits = (__ballot_sync(gmask, contrib) >> gshift) & ((GS == 32) ? 0xffffffffu : ((1u << GS) - 1u));
+                    while (bits) {
+                        const int q = __ffs(bits) - 1;
+                        bits &= bits - 1u;
+                        row_body(base + q);
+                    }
+                }
+            } else {
+                for (int r_ = 0; r_ < rc; r_++) row_body(r_);
             }
         }
         if (fast_cost && !term) {
@@ -1848,16 +1880,30 @@ TOB_DEV double knot_al_cost_at(const DevProblem& P, int k, const double* lamk, c
         // large constraint sets (car_escape: 177 rows per knot; multipliers in global memory): four rows at a time with every
         // load issued before the first use -- the one-row-at-a-time loop paid a dependent load + branch chain of ~340 cycles
         // per row (profiles/r01e3).  Same per-row expressions, same accumulation order.
+        // the multipliers / penalties of the NEXT four rows are requested before the current four are used (they come from L2;
+        // the rows themselves sit in shared memory): one warp per SMSP has nothing else to hide that latency with
+        double ln[4], mn[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            ln[q] = (q < rc) ? __ldg(lamk + q) : 0.0;
+            mn[q] = (q < rc) ? __ldg(muk + q) : 0.0;
+        }
         for (; i + 4 <= rc; i += 4) {
             double l4[4], m4[4], c4[4], ra[4], rb_[4], rr[4];
             int eq4[4], kind4[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { l4[q] = ln[q]; m4[q] = mn[q]; }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int nx = i + 4 + q;
+                ln[q] = (nx < rc) ? __ldg(lamk + nx) : 0.0;
+                mn[q] = (nx < rc) ? __ldg(muk + nx) : 0.0;
+            }
 #pragma unroll
             for (int q = 0; q < 4; q++) {  // every load of the four rows first
                 const DevRow* r = &P.rows[rb + i + q];
                 kind4[q] = r->kind; eq4[q] = r->eq;
                 ra[q] = r->a; rb_[q] = r->b; rr[q] = r->r;
-                l4[q] = __ldg(lamk + i + q);
-                m4[q] = __ldg(muk + i + q);
             }
 #pragma unroll
             for (int q = 0; q < 4; q++) {  // circle rows (the bulk of such sets) without a branch: four independent chains
@@ -2479,7 +2525,10 @@ template <class C> LsBpFn ls_bp_cta_variant(int minb) {
 }
 
 template <class C> constexpr int ls_res_threads() {
-    return ls_bp_cta_threads<C>() > 32 * RollRoles<C>::R ? ls_bp_cta_threads<C>() : 32 * RollRoles<C>::R;
+    // 256 threads for every model: the Riccati recursion of a small model needs only 64, but the knot-parallel phases (Jacobians,
+    // expansion, the cost of all step sizes) of a problem with a large constraint set (car_escape: 177 rows per knot) were
+    // 2 warps walking 101 knots (profiles/r02k: T2 47 % of the iteration)
+    return 256;
 }
 typedef void (*LsResFn)(const DevProblem, const DevBatch, const DevCtl, const LsCtl, const int);
 template <class C> LsResFn ls_resident_variant(int minb) {

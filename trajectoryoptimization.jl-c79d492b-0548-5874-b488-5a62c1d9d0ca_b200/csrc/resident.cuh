@@ -292,6 +292,41 @@ __device__ __noinline__ void res_phase_costs(const DevProblem& P, double* ws, co
     const int N = P.N;
     const double* lam = ws + L.LAM;
     const double* mu = ws + L.MU;
+    // Large constraint sets (car_escape: 177 rows per knot): one WARP per knot, lane = step size -- the knot's rows / multipliers /
+    // penalties are then the same for every lane (broadcast loads instead of 21 private walks through them), and the candidates
+    // of a knot are interleaved by step size (one coalesced load per element)
+    bool big = false;
+    if (al_on) {
+        for (int k = 0; k < N; k++) big = big || (P.knot_row_count[k] > RolloutStage<C>::LC);
+    }
+    if (big) {
+        const int lane = tid & 31, warp = tid >> 5;
+        const int t = lane;
+        for (int k = warp; k < N; k += NT / 32) {
+            if (t >= ntrial || !fl.okf[t]) continue;
+            double x[n], u[m];
+#pragma unroll
+            for (int i = 0; i < n; i++) x[i] = XB[cand_index((size_t)k * n + i, t, 32)];
+            double cs, ca = 0.0;
+            if (k < N - 1) {
+#pragma unroll
+                for (int i = 0; i < m; i++) u[i] = UB[cand_index((size_t)k * m + i, t, 32)];
+                cs = stage_cost<C>(P, x, u);
+                if (al_on) {
+                    const int lo = P.knot_lam_off[k];
+                    ca = knot_al_cost_at<C>(P, k, lam + lo, mu + lo, x, u);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < m; i++) u[i] = 0.0;
+                cs = term_cost<C>(P, x);
+                if (al_on) ca = knot_al_cost<C>(P, N - 1, lam, mu, x, u);
+            }
+            cst[k * 32 + t] = cs;
+            cal[k * 32 + t] = ca;
+        }
+        return;
+    }
     for (int it = tid; it < N * ntrial; it += NT) {
         const int k = it / ntrial, t = it - k * ntrial;
         if (!fl.okf[t]) continue;
