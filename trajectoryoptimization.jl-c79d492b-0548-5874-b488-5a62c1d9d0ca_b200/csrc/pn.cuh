@@ -30,7 +30,7 @@ template <class C> struct PnDims {
 // per-slot scratch in global memory (doubles); the int tables sit at the end
 template <class C>
 struct PnLayout {
-    unsigned long long Xb, Ub, Xn, Un, fv, Cv, Gc, y, dl, t, rr, sx, dx, Sd, Ld, Lo, ints, total;
+    unsigned long long Xb, Ub, Xn, Un, fv, Cv, Gc, y, dl, t, rr, sx, dx, rd, Sd, Ld, Lo, ints, total;
     // ints: act[Ptot], pa[N], aidx[N][LS_PN_PA], rblk[N+1]
 };
 template <class C>
@@ -46,6 +46,7 @@ __host__ __device__ inline PnLayout<C> pn_layout(int N, int Ptot) {
     L.Cv = o; o += (unsigned long long)Ptot;
     L.Gc = o; o += (unsigned long long)N * LS_PN_PA * (D::n + D::m);
     L.y = o; o += nb;  L.dl = o; o += nb;  L.t = o; o += nb;  L.rr = o; o += nb;  L.sx = o; o += nb;  L.dx = o; o += nb;
+    L.rd = o; o += nb;  // 1 / diag(L) of every block (exact reciprocals: the triangular solves divide through div_by)
     L.Sd = o; o += (unsigned long long)(N + 1) * D::RR;
     L.Ld = o; o += (unsigned long long)(N + 1) * D::RR;
     L.Lo = o; o += (unsigned long long)(N + 1) * D::RR;
@@ -290,6 +291,7 @@ struct PnCtx {
             if (!sm.flag) return false;
             double* Ld = sc + PL.Ld + (size_t)s * RR;
             for (int e = tid; e < r * r; e += NT) { Ld[e] = sm.A[e]; sm.Lp[e] = sm.A[e]; }
+            for (int i = tid; i < r; i += NT) sc[PL.rd + (size_t)s * R + i] = 1.0 / sm.A[i * r + i];
             rp = r;
             __syncthreads();
         }
@@ -315,17 +317,19 @@ struct PnCtx {
             } else {
                 for (int i = tid; i < r; i += NT) sm.vec[i] = b[i];
             }
+            for (int e = tid; e < r * r; e += NT) sm.A[e] = Ld[e];   // the block's factor: shared memory for the serial solve
+            for (int i = tid; i < r; i += NT) sm.vec[R + i] = sc[PL.rd + (size_t)s * R + i];
             __syncthreads();
-            // triangular solve by the first warp: row i's sum runs over l = 0..i-1 in order, as in the oracle
+            // triangular solve by the first warp: row i's sum runs over l = 0..i-1 in order, as in the oracle; the division by
+            // the diagonal goes through its exact reciprocal (div_by: bitwise the IEEE quotient, a third of its latency)
             if (tid < 32) {
                 double v0 = (tid < r) ? sm.vec[tid] : 0.0, v1 = (tid + 32 < r) ? sm.vec[tid + 32] : 0.0;
                 for (int l = 0; l < r; l++) {
-                    const double dl_ = Ld[l * r + l];
                     double tl = (l < 32) ? v0 : v1;
-                    tl = __shfl_sync(0xffffffffu, tl, l & 31) / dl_;
+                    tl = div_by(__shfl_sync(0xffffffffu, tl, l & 31), sm.A[l * r + l], sm.vec[R + l]);
                     if (tid == (l & 31)) { if (l < 32) v0 = tl; else v1 = tl; }
-                    if (tid > l && tid < r) v0 = fma(-Ld[tid * r + l], tl, v0);
-                    if (tid + 32 > l && tid + 32 < r) v1 = fma(-Ld[(tid + 32) * r + l], tl, v1);
+                    if (tid > l && tid < r) v0 = fma(-sm.A[tid * r + l], tl, v0);
+                    if (tid + 32 > l && tid + 32 < r) v1 = fma(-sm.A[(tid + 32) * r + l], tl, v1);
                 }
                 if (tid < r) t[s * R + tid] = v0;
                 if (tid + 32 < r) t[s * R + tid + 32] = v1;
@@ -347,16 +351,17 @@ struct PnCtx {
             } else {
                 for (int i = tid; i < r; i += NT) sm.vec[i] = t[s * R + i];
             }
+            for (int e = tid; e < r * r; e += NT) sm.A[e] = Ld[e];
+            for (int i = tid; i < r; i += NT) sm.vec[R + i] = sc[PL.rd + (size_t)s * R + i];
             __syncthreads();
             if (tid < 32) {
                 double v0 = (tid < r) ? sm.vec[tid] : 0.0, v1 = (tid + 32 < r) ? sm.vec[tid + 32] : 0.0;
                 for (int l = r - 1; l >= 0; l--) {
-                    const double dl_ = Ld[l * r + l];
                     double xl = (l < 32) ? v0 : v1;
-                    xl = __shfl_sync(0xffffffffu, xl, l & 31) / dl_;
+                    xl = div_by(__shfl_sync(0xffffffffu, xl, l & 31), sm.A[l * r + l], sm.vec[R + l]);
                     if (tid == (l & 31)) { if (l < 32) v0 = xl; else v1 = xl; }
-                    if (tid < l) v0 = fma(-Ld[l * r + tid], xl, v0);
-                    if (tid + 32 < l) v1 = fma(-Ld[l * r + tid + 32], xl, v1);
+                    if (tid < l) v0 = fma(-sm.A[l * r + tid], xl, v0);
+                    if (tid + 32 < l) v1 = fma(-sm.A[l * r + tid + 32], xl, v1);
                 }
                 if (tid < r) x[s * R + tid] = v0;
                 if (tid + 32 < r) x[s * R + tid + 32] = v1;
