@@ -109,7 +109,16 @@ typedef struct TOiLQROptions {          /* src/solvers/ilqr/ilqr_solver.jl:7-81 
     double  max_cost_value;             /* 1e8 */
     double  max_state_value;            /* 1e8 */
     double  max_control_value;          /* 1e8 */
+    int32_t bp_reg_type;                /* TO_REG_CONTROL (:control): Quu + rho I; TO_REG_STATE (:state): Quu + rho B'B, Qux + rho B'A
+                                           (backward_pass.jl:38-46).  :state runs on the CTA-per-problem backward pass. */
+    int32_t gradient_type;              /* TO_GRAD_TODOROV (default), _FEEDFORWARD, _L2, _LINF (ilqr_methods.jl:91-137) */
 } TOiLQROptions;
+#define TO_REG_CONTROL 0
+#define TO_REG_STATE   1
+#define TO_GRAD_TODOROV     0
+#define TO_GRAD_FEEDFORWARD 1
+#define TO_GRAD_L2          2
+#define TO_GRAD_LINF        3
 
 typedef struct TOALOptions {            /* src/solvers/augmented_lagrangian/augmented_lagrangian_solver.jl:8-66 */
     TOiLQROptions opts_uncon;

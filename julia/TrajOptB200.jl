@@ -43,6 +43,7 @@ struct TOiLQROptions
     line_search_lower_bound::Float64; line_search_upper_bound::Float64
     bp_reg_increase_factor::Float64; bp_reg_max::Float64; bp_reg_min::Float64; bp_reg_fp::Float64
     max_cost_value::Float64; max_state_value::Float64; max_control_value::Float64
+    bp_reg_type::Int32; gradient_type::Int32
 end
 struct TOALOptions
     opts_uncon::TOiLQROptions
@@ -181,16 +182,19 @@ function marshal(prob::TO.Problem)
 end
 
 # ---- options ------------------------------------------------------------------------------------------
-# bp_reg_type / gradient_type: only the reference defaults (:control, :todorov) are on the device path (no test, benchmark or
-# example of the reference sets anything else); refuse the others instead of silently ignoring them
-function check_fixed(o::TO.iLQRSolverOptions)
-    o.bp_reg_type == :control || error("TrajOptB200: bp_reg_type=$(o.bp_reg_type) is not on the device path (only :control)")
-    o.gradient_type == :todorov || error("TrajOptB200: gradient_type=$(o.gradient_type) is not on the device path (only :todorov)")
-    o
+# bp_reg_type / gradient_type (ilqr_solver.jl:47-52,76-80) as the ABI's enums
+const REG_TYPES = Dict(:control => Int32(0), :state => Int32(1))
+const GRAD_TYPES = Dict(:todorov => Int32(0), :feedforward => Int32(1), :ℓ2 => Int32(2), :ℓinf => Int32(3))
+function c_opts(o::TO.iLQRSolverOptions)
+    haskey(REG_TYPES, o.bp_reg_type) || error("TrajOptB200: unknown bp_reg_type $(o.bp_reg_type)")
+    haskey(GRAD_TYPES, o.gradient_type) || error("TrajOptB200: unknown gradient_type $(o.gradient_type)")
+    (o.bp_reg_type == :state && o.square_root) &&
+        error("TrajOptB200: bp_reg_type=:state with square_root=true is not on the device path")
+    TOiLQROptions(o.cost_tolerance, o.gradient_norm_tolerance, o.iterations, o.dJ_counter_limit,
+        o.square_root, o.iterations_linesearch, o.line_search_lower_bound, o.line_search_upper_bound, o.bp_reg_increase_factor,
+        o.bp_reg_max, o.bp_reg_min, o.bp_reg_fp, o.max_cost_value, o.max_state_value, o.max_control_value,
+        REG_TYPES[o.bp_reg_type], GRAD_TYPES[o.gradient_type])
 end
-c_opts(o::TO.iLQRSolverOptions) = (check_fixed(o); TOiLQROptions(o.cost_tolerance, o.gradient_norm_tolerance, o.iterations, o.dJ_counter_limit,
-    o.square_root, o.iterations_linesearch, o.line_search_lower_bound, o.line_search_upper_bound, o.bp_reg_increase_factor,
-    o.bp_reg_max, o.bp_reg_min, o.bp_reg_fp, o.max_cost_value, o.max_state_value, o.max_control_value))
 c_opts(o::TO.AugmentedLagrangianSolverOptions) = TOALOptions(c_opts(o.opts_uncon), o.cost_tolerance, o.cost_tolerance_intermediate,
     o.gradient_norm_tolerance, o.gradient_norm_tolerance_intermediate, o.constraint_tolerance, o.iterations,
     o.kickout_max_penalty, o.dual_min, o.dual_max, o.penalty_max, o.penalty_initial, o.penalty_scaling)

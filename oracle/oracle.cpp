@@ -650,6 +650,7 @@ static bool backwardpass(const Spec& S, ILQR& s, double dV[2]) {
     dV[0] = dV[1] = 0.0;
     vec T(n * n), Tu(m * n), M(n * n), Mu(m * m), Mux(m * n), v(n), vu(m);
     vec Quu_reg(m * m), Kk(m * n), dk(m), KQ(n * m), M1(n * n), M2(n * n), M3(n * n), v1(n), v2(n), v3(n), Uc(m * m);
+    vec RB(m * n), Qux_r(m * n);
     int k = N - 2;
     while (k >= 0) {
         const double* A = s.A[k].data();
@@ -670,8 +671,19 @@ static bool backwardpass(const Spec& S, ILQR& s, double dV[2]) {
         mul_AB(Tu.data(), m, n, A, n, Mux.data());
         for (int i = 0; i < m * n; i++) Q.ux[i] += Mux[i];
 
-        for (int i = 0; i < m * m; i++) Quu_reg[i] = Q.uu[i];
-        for (int i = 0; i < m; i++) Quu_reg[i * m + i] = Q.uu[i * m + i] + s.rho * 1.0;
+        const double* Qux_reg = Q.ux.data();
+        if (s.o.bp_reg_type == TO_REG_STATE) {
+            // backward_pass.jl:38-41: Quu_reg = Q.uu + rho*fdu'*fdu, Qux_reg = Q.ux + rho*fdu'*fdx -- (rho*B') first, then the product
+            for (int l = 0; l < n; l++) for (int i = 0; i < m; i++) RB[l * m + i] = s.rho * B[i * n + l];   // m×n, col-major
+            mul_AB(RB.data(), m, n, B, m, Mu.data());
+            for (int i = 0; i < m * m; i++) Quu_reg[i] = Q.uu[i] + Mu[i];
+            mul_AB(RB.data(), m, n, A, n, Mux.data());
+            for (int i = 0; i < m * n; i++) Qux_r[i] = Q.ux[i] + Mux[i];
+            Qux_reg = Qux_r.data();
+        } else {
+            for (int i = 0; i < m * m; i++) Quu_reg[i] = Q.uu[i];
+            for (int i = 0; i < m; i++) Quu_reg[i * m + i] = Q.uu[i * m + i] + s.rho * 1.0;
+        }
         if (!chol_upper(Quu_reg.data(), m, Uc.data())) {
             if (!std::isfinite(s.rho)) return false;
             reg_update(s, true);
@@ -679,7 +691,7 @@ static bool backwardpass(const Spec& S, ILQR& s, double dV[2]) {
             dV[0] = dV[1] = 0.0;
             continue;
         }
-        solve_general(Quu_reg.data(), m, Q.ux.data(), n, Kk.data());
+        solve_general(Quu_reg.data(), m, Qux_reg, n, Kk.data());
         for (int i = 0; i < m * n; i++) Kk[i] = -1.0 * Kk[i];
         solve_general(Quu_reg.data(), m, Q.u.data(), 1, dk.data());
         for (int i = 0; i < m; i++) dk[i] = -1.0 * dk[i];
@@ -892,6 +904,31 @@ static double gradient_todorov(const Spec& S, const ILQR& s, const Prob& p) {
     return sum / (double)S.N;
 }
 
+// norm(v) of a short Vector{Float64} (LinearAlgebra generic_norm2, Julia 1.1 generic.jl: BLAS nrm2 only from 32 elements on)
+static double julia_norm2(const double* v, int len) {
+    double maxabs = 0.0;  // generic_normInf
+    for (int i = 0; i < len; i++) { double a = std::fabs(v[i]); maxabs = (maxabs != maxabs || maxabs > a) ? maxabs : a; }
+    if (maxabs == 0.0 || std::isinf(maxabs)) return maxabs;
+    if (std::isfinite((double)len * maxabs * maxabs) && maxabs * maxabs != 0.0) {
+        double sum = 0.0;
+        for (int i = 0; i < len; i++) sum += v[i] * v[i];
+        return std::sqrt(sum);
+    }
+    double inv = 1.0 / maxabs, sum = 0.0;
+    for (int i = 0; i < len; i++) { double t = std::fabs(v[i]) * inv; sum += t * t; }
+    return maxabs * std::sqrt(sum);
+}
+// gradient_feedforward (ilqr_methods.jl:133-137): norm(solver.d, Inf) over a vector of vectors = the largest 2-norm of a d[k]
+// (generic_normInf applies `norm` to each element)
+static double gradient_feedforward(const Spec& S, const ILQR& s) {
+    double maxabs = 0.0;
+    for (int k = 0; k < S.N - 1; k++) {
+        const double a = julia_norm2(s.d[k].data(), S.m);
+        maxabs = (k == 0) ? a : ((maxabs != maxabs || maxabs > a) ? maxabs : a);
+    }
+    return maxabs;
+}
+
 struct Ctx {
     const Spec* S;
     Prob p;
@@ -948,7 +985,34 @@ static void record_inner(Ctx& c, double J, double dJ) {
     s.iterations += 1;
     s.last_cost = J;
     s.last_dJ = dJ;
-    s.last_grad = gradient_todorov(*c.S, s, c.p);
+    // calculate_gradient (ilqr_methods.jl:91-102)
+    if (s.o.gradient_type == TO_GRAD_FEEDFORWARD) {
+        s.last_grad = gradient_feedforward(*c.S, s);
+    } else if (s.o.gradient_type == TO_GRAD_L2 || s.o.gradient_type == TO_GRAD_LINF) {
+        // compute_gradient (:104-116): the (non-square-root) cost expansion at the current X, U; its first-order parts stacked
+        // [Q1.x; Q1.u; ...; QN.x].  norm(g, Inf) is exact; norm(g) is BLAS nrm2 in the reference (more than 32 elements), whose
+        // internal accumulation is OpenBLAS's -- restated as the plain sequential sum of squares ("parity unpinned" at the last bit)
+        const int sq = s.o.square_root;
+        s.o.square_root = 0;
+        cost_expansion(*c.S, s, c.al, c.p);
+        s.o.square_root = sq;
+        const Spec& S = *c.S;
+        double mx = 0.0, sum = 0.0;
+        bool first = true;
+        auto take = [&](double v) {
+            const double a = std::fabs(v);
+            mx = first ? a : ((mx != mx || mx > a) ? mx : a);
+            first = false;
+            sum += v * v;
+        };
+        for (int k = 0; k < S.N; k++) {
+            for (int i = 0; i < S.n; i++) take(s.Q[k].x[i]);
+            if (k < S.N - 1) for (int i = 0; i < S.m; i++) take(s.Q[k].u[i]);
+        }
+        s.last_grad = (s.o.gradient_type == TO_GRAD_LINF) ? mx : std::sqrt(sum);
+    } else {
+        s.last_grad = gradient_todorov(*c.S, s, c.p);
+    }
     if (dJ == 0.0) s.dJ_zero += 1; else s.dJ_zero = 0;
     if (c.tr) {
         TOIterRecord r;
@@ -1447,6 +1511,7 @@ void oracle_default_ilqr_options(TOiLQROptions* o) {
     o->square_root = 0; o->iterations_linesearch = 20; o->line_search_lower_bound = 1e-8; o->line_search_upper_bound = 10.0;
     o->bp_reg_increase_factor = 1.6; o->bp_reg_max = 1e8; o->bp_reg_min = 1e-8; o->bp_reg_fp = 10.0;
     o->max_cost_value = 1e8; o->max_state_value = 1e8; o->max_control_value = 1e8;
+    o->bp_reg_type = TO_REG_CONTROL; o->gradient_type = TO_GRAD_TODOROV;
 }
 void oracle_default_al_options(TOALOptions* o) {
     oracle_default_ilqr_options(&o->opts_uncon);

@@ -23,11 +23,18 @@ def test_unknown_option_is_an_error():
 
 
 def test_reference_options_outside_the_device_path_are_refused():
-    to.iLQRSolverOptions(bp_reg_type=":control", gradient_type=":todorov").to_c()   # the defaults, in Julia symbol spelling
+    c = to.iLQRSolverOptions(bp_reg_type=":control", gradient_type=":todorov").to_c()   # the defaults, in Julia symbol spelling
+    assert (c.bp_reg_type, c.gradient_type) == (0, 0)
     to.iLQRSolverOptions(bp_reg_initial=1.0, bp_sqrt_inv_type=":pseudo").to_c()     # declared but read nowhere in the reference
-    for kw in (dict(bp_reg_type=":state"), dict(gradient_type=":feedforward"), dict(gradient_type="l2")):
-        with pytest.raises(NotImplementedError, match="not on the device path"):
-            to.iLQRSolverOptions(**kw).to_c()
+    # ilqr_solver.jl:47-52,76-80: the other regularisation / gradient types map onto the ABI's enums
+    for kw, want in ((dict(bp_reg_type=":state"), (1, 0)), (dict(gradient_type=":feedforward"), (0, 1)),
+                     (dict(gradient_type="l2"), (0, 2)), (dict(gradient_type=":ℓinf"), (0, 3))):
+        c = to.iLQRSolverOptions(**kw).to_c()
+        assert (c.bp_reg_type, c.gradient_type) == want
+    with pytest.raises(ValueError, match="expected one of"):
+        to.iLQRSolverOptions(gradient_type=":newton").to_c()
+    with pytest.raises(NotImplementedError, match="not on the device path"):
+        to.iLQRSolverOptions(bp_reg_type=":state", square_root=True).to_c()
     with pytest.raises(NotImplementedError, match="solve_type"):
         to.ALTROSolverOptions(projected_newton=True, opts_pn=to.ProjectedNewtonSolverOptions(solve_type=":optimal")).to_c()
 

@@ -45,7 +45,8 @@ class TOiLQROptions(C.Structure):
                 ("iterations_linesearch", C.c_int32), ("line_search_lower_bound", C.c_double),
                 ("line_search_upper_bound", C.c_double), ("bp_reg_increase_factor", C.c_double),
                 ("bp_reg_max", C.c_double), ("bp_reg_min", C.c_double), ("bp_reg_fp", C.c_double),
-                ("max_cost_value", C.c_double), ("max_state_value", C.c_double), ("max_control_value", C.c_double)]
+                ("max_cost_value", C.c_double), ("max_state_value", C.c_double), ("max_control_value", C.c_double),
+                ("bp_reg_type", C.c_int32), ("gradient_type", C.c_int32)]
 
 
 class TOALOptions(C.Structure):

@@ -302,30 +302,34 @@ class iLQRSolverOptions(_Opts):
                      line_search_upper_bound=10.0, bp_reg_increase_factor=1.6, bp_reg_max=1e8, bp_reg_min=1e-8,
                      bp_reg_fp=10.0, max_cost_value=1e8, max_state_value=1e8, max_control_value=1e8)
 
-    # options of ilqr_solver.jl:7-81 that exist in the reference but are never set by its tests, benchmarks or examples:
-    # only their default values are on the device path; anything else is refused, not silently ignored
-    _fixed = dict(bp_reg_type="control", gradient_type="todorov")
+    # symbol-valued options (ilqr_solver.jl:47-52,76-80), spelled as in Julia (":state") or bare ("state")
+    _symbols = dict(bp_reg_type=dict(control=0, state=1),
+                    gradient_type={"todorov": 0, "feedforward": 1, "ℓ2": 2, "l2": 2, "ℓinf": 3, "linf": 3})
     _ignored = ("bp_reg_initial", "bp_sqrt_inv_type")  # declared at ilqr_solver.jl:45,64 and read nowhere in the reference
 
     def __init__(self, **kw):
         for k in self._ignored:
             kw.pop(k, None)
-        fixed = {k: kw.pop(k) for k in list(kw) if k in self._fixed}
+        sym = {k: kw.pop(k) for k in list(kw) if k in self._symbols}
         super().__init__(**kw)
-        for k, v in self._fixed.items():
-            setattr(self, k, fixed.get(k, v))
+        self.bp_reg_type = sym.get("bp_reg_type", "control")
+        self.gradient_type = sym.get("gradient_type", "todorov")
 
     def to_c(self):
-        for k, v in self._fixed.items():
-            got = getattr(self, k)
-            got = got.lstrip(":") if isinstance(got, str) else got
-            if got != v:
-                raise NotImplementedError("iLQRSolverOptions.%s=%r is not on the device path (only the reference default %r)" % (k, got, v))
         o = abi.TOiLQROptions()
         ints = ("iterations", "dJ_counter_limit", "square_root", "iterations_linesearch")
         for k in self._defaults:
             v = getattr(self, k)
             setattr(o, k, int(v) if k in ints else float(v))
+        for k, table in self._symbols.items():
+            got = getattr(self, k)
+            got = got.lstrip(":") if isinstance(got, str) else got
+            if got not in table:
+                raise ValueError("iLQRSolverOptions.%s=%r: expected one of %s" % (k, got, sorted(table)))
+            setattr(o, k, table[got])
+        if o.bp_reg_type == 1 and o.square_root:
+            raise NotImplementedError("bp_reg_type=:state with square_root=true is not on the device path (the square-root pass "
+                                      "regularises with :control only)")
         return o
 
 

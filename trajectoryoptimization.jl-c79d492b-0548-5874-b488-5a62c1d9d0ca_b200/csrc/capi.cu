@@ -503,6 +503,9 @@ int run_lockstep_impl(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl&
     }
     unsigned int res_waves = (max_rows > 32) ? 2u : 1u;
     if (const char* env = getenv("TRAJOPT_B200_RESIDENT_WAVES")) res_waves = (unsigned int)std::max(1, std::min(4, atoi(env)));
+    if (c.o.opts_uncon.gradient_type != TO_GRAD_TODOROV && (!v.cand_bulk || !v.cand_alloc))
+        return s->fail(TO_ERR_UNSUPPORTED, "gradient_type other than :todorov needs the candidate buffers of the line search "
+                                           "(not enough device memory, or TRAJOPT_B200_BULK_CANDIDATES=0)");
     const unsigned int res_threshold = (!c.o.opts_uncon.square_root && ntrial <= 32 && v.cand_alloc) ? std::min(v.res_slots * res_waves, v.cand_slots) : 0u;
     for (long long t = 0; t < max_ticks; t++) {
         const int cur = (int)(t & 1);
@@ -535,7 +538,8 @@ int run_lockstep_impl(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl&
         }
         v.ki->ls_launch(LS_PHASE_JAC, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
         mark();
-        const bool bp_cta = !c.o.opts_uncon.square_root && known_active <= cta_threshold;
+        // bp_reg_type = :state is implemented by the CTA-per-problem pass (and the resident kernel) only
+        const bool bp_cta = !c.o.opts_uncon.square_root && (known_active <= cta_threshold || c.o.opts_uncon.bp_reg_type == TO_REG_STATE);
         if (bp_cta) {
             // latency path: knot-parallel expansion, then one CTA per problem for the recursion
             v.ki->ls_launch(LS_PHASE_EXPAND, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
@@ -683,6 +687,10 @@ int check_opts(TOSolver* s, const TOALOptions& o) {
     if (io.square_root && s->engine != 1)
         return s->fail(TO_ERR_UNSUPPORTED, "the square-root backward pass runs on the lockstep engine only (unset TRAJOPT_B200_ENGINE)");
     if (!s->batch_set) return s->fail(TO_ERR_INVALID, "to_set_batch has not been called");
+    if (io.bp_reg_type != TO_REG_CONTROL && io.bp_reg_type != TO_REG_STATE) return s->fail(TO_ERR_INVALID, "unknown bp_reg_type");
+    if (io.gradient_type < TO_GRAD_TODOROV || io.gradient_type > TO_GRAD_LINF) return s->fail(TO_ERR_INVALID, "unknown gradient_type");
+    if (io.bp_reg_type == TO_REG_STATE && io.square_root)
+        return s->fail(TO_ERR_UNSUPPORTED, "bp_reg_type = :state with the square-root backward pass is not on the device path");
     return 0;
 }
 
@@ -771,6 +779,7 @@ void to_default_ilqr_options(TOiLQROptions* o) {
     o->square_root = 0; o->iterations_linesearch = 20; o->line_search_lower_bound = 1e-8; o->line_search_upper_bound = 10.0;
     o->bp_reg_increase_factor = 1.6; o->bp_reg_max = 1e8; o->bp_reg_min = 1e-8; o->bp_reg_fp = 10.0;
     o->max_cost_value = 1e8; o->max_state_value = 1e8; o->max_control_value = 1e8;
+    o->bp_reg_type = TO_REG_CONTROL; o->gradient_type = TO_GRAD_TODOROV;
 }
 void to_default_al_options(TOALOptions* o) {
     to_default_ilqr_options(&o->opts_uncon);

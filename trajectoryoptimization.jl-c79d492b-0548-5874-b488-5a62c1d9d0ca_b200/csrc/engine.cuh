@@ -365,8 +365,59 @@ struct Solver {
         __syncwarp();
     }
 
-    // ---- Todorov gradient (ilqr_methods.jl:122-129): mean over N of max_i |d_i|/(|u_i|+1) ----
+    // ---- calculate_gradient (ilqr_methods.jl:91-102) ----
     __device__ double gradient() {
+        if (io.gradient_type == TO_GRAD_FEEDFORWARD) return gradient_feedforward();
+        if (io.gradient_type == TO_GRAD_L2 || io.gradient_type == TO_GRAD_LINF) return gradient_cost(io.gradient_type == TO_GRAD_LINF);
+        return gradient_todorov();
+    }
+    // norm(v) of a short Vector{Float64}: LinearAlgebra.generic_norm2 (Julia 1.1 generic.jl; BLAS nrm2 only from 32 elements on)
+    __device__ static double julia_norm2(const double* v, int len) {
+        double maxabs = 0.0;
+        for (int i = 0; i < len; i++) { const double a = fabs(v[i]); maxabs = (maxabs != maxabs || maxabs > a) ? maxabs : a; }
+        if (maxabs == 0.0 || isinf(maxabs)) return maxabs;
+        if (isfinite((double)len * maxabs * maxabs) && maxabs * maxabs != 0.0) {
+            double sum = 0.0;
+            for (int i = 0; i < len; i++) sum += v[i] * v[i];
+            return sqrt(sum);
+        }
+        const double inv = 1.0 / maxabs;
+        double sum = 0.0;
+        for (int i = 0; i < len; i++) { const double t = fabs(v[i]) * inv; sum += t * t; }
+        return maxabs * sqrt(sum);
+    }
+    // gradient_feedforward (ilqr_methods.jl:133-137): norm(solver.d, Inf) over a vector of vectors = the largest 2-norm of a d[k]
+    __device__ double gradient_feedforward() {
+        const int N = P.N;
+        double* cb = CB();
+        for (int k = lane; k < N - 1; k += 32) cb[k] = julia_norm2(KD(k) + C::m * C::n, C::m);
+        __syncwarp();
+        double mx = 0.0;
+        for (int k = 0; k < N - 1; k++) { const double a = cb[k]; mx = (k == 0) ? a : ((mx != mx || mx > a) ? mx : a); }
+        __syncwarp();
+        return mx;
+    }
+    // :ℓ2 / :ℓinf (ilqr_methods.jl:97-116): norm of [Q1.x; Q1.u; ...; QN.x] of the cost expansion at the current X, U
+    __device__ double gradient_cost(bool inf_norm) {
+        const int N = P.N;
+        double mx = 0.0, sum = 0.0;
+        bool first = true;
+        for (int k = 0; k < N; k++) {
+            expansion(k);  // ends with __syncwarp; lane 0 folds the knot's entries in order
+            const int cnt = (k < N - 1) ? C::n + C::m : C::n;
+            for (int e = 0; e < cnt; e++) {
+                const double v = (e < C::n) ? sm.Qx[e] : sm.Qu[e - C::n];
+                const double a = fabs(v);
+                mx = first ? a : ((mx != mx || mx > a) ? mx : a);
+                first = false;
+                sum += v * v;
+            }
+            __syncwarp();
+        }
+        return inf_norm ? mx : sqrt(sum);
+    }
+    // ---- Todorov gradient (ilqr_methods.jl:122-129): mean over N of max_i |d_i|/(|u_i|+1) ----
+    __device__ double gradient_todorov() {
         const int N = P.N;
         double* cb = CB();
         const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
@@ -830,12 +881,25 @@ struct Solver {
                     }
                     if (k < stored_from) stored_from = k;
                 }
-                // Quu_reg = Quu + ρI, replicated in registers
+                // Quu_reg = Quu + ρI (:control) or Quu + (ρB')B with Qux_reg = Qux + (ρB')A (:state, backward_pass.jl:38-46),
+                // replicated in registers
+                const bool reg_state = (io.bp_reg_type == TO_REG_STATE);
                 LU f;
+                if (reg_state) {
 #pragma unroll
-                for (int e = 0; e < m * m; e++) f.a[e] = sm.Quu[e];
+                    for (int e = 0; e < m * m; e++) {
+                        const int i = e % m, j = e / m;
+                        double acc = 0.0;
 #pragma unroll
-                for (int i = 0; i < m; i++) f.a[i * m + i] = sm.Quu[i * m + i] + rho * 1.0;
+                        for (int l = 0; l < n; l++) acc = fma(rho * sm.B[i * n + l], sm.B[j * n + l], acc);
+                        f.a[e] = sm.Quu[e] + acc;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < m * m; e++) f.a[e] = sm.Quu[e];
+#pragma unroll
+                    for (int i = 0; i < m; i++) f.a[i * m + i] = sm.Quu[i * m + i] + rho * 1.0;
+                }
                 if (!chol_pd(f.a)) { failed = true; break; }
                 lu_factor(f);
                 // gains: lane c < n solves for column c of K, lane n for d
@@ -843,6 +907,15 @@ struct Solver {
                     double rhs[m];
 #pragma unroll
                     for (int i = 0; i < m; i++) rhs[i] = (lane < n) ? sm.Qux[lane * m + i] : sm.Qu[i];
+                    if (reg_state && lane < n) {
+#pragma unroll
+                        for (int i = 0; i < m; i++) {
+                            double acc = 0.0;
+#pragma unroll
+                            for (int l = 0; l < n; l++) acc = fma(rho * sm.B[i * n + l], sm.A[lane * n + l], acc);
+                            rhs[i] = sm.Qux[lane * m + i] + acc;
+                        }
+                    }
                     lu_solve(f, rhs);
 #pragma unroll
                     for (int i = 0; i < m; i++) {

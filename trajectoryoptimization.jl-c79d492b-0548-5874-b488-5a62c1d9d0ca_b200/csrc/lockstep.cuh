@@ -1480,6 +1480,39 @@ __device__ __forceinline__ void ls_bp_cta_problem(const DevProblem& P, const TOi
             const double* q = ws + L.QST + (size_t)k * C::QS;
             for (int e = tid; e < C::QS; e += NT) cp_async8(&sm.Q[buf][e], q + e);
         };
+        // bp_reg_type = :state (backward_pass.jl:38-46): Quu_reg = Quu + (rho B')B, Qux_reg = Qux + (rho B')A, each thread forms
+        // what it needs from the knot's [A B] in shared memory (the same sums as the oracle: (rho*B(l,i)) first, l ascending)
+        const bool reg_state = (io.bp_reg_type == TO_REG_STATE);
+        auto quu_reg = [&](double* a, const double* AB, const double* Quu) {
+            if (reg_state) {
+#pragma unroll
+                for (int e = 0; e < m * m; e++) {
+                    const int i = e % m, j = e / m;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < n; l++) acc = fma(rho * AB[l * LDZ + n + i], AB[l * LDZ + n + j], acc);
+                    a[e] = Quu[e] + acc;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < m * m; e++) a[e] = Quu[e];
+#pragma unroll
+                for (int i = 0; i < m; i++) a[i * m + i] = Quu[i * m + i] + rho * 1.0;
+            }
+        };
+        auto qux_reg_col = [&](double* rhs, const double* AB, const double* Quxcol, int col) {
+#pragma unroll
+            for (int i = 0; i < m; i++) {
+                double v = Quxcol[i];
+                if (reg_state) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < n; l++) acc = fma(rho * AB[l * LDZ + n + i], AB[l * LDZ + col], acc);
+                    v = Quxcol[i] + acc;
+                }
+                rhs[i] = v;
+            }
+        };
         bool store_mode = false, ok = true;
         double dV0 = 0.0, dV1 = 0.0;  // kept by thread NT-1
         for (;;) {
@@ -1582,10 +1615,7 @@ __device__ __forceinline__ void ls_bp_cta_problem(const DevProblem& P, const TOi
                         __syncwarp();
                         LU f;
                         if (lane <= n) {
-#pragma unroll
-                            for (int q = 0; q < m * m; q++) f.a[q] = sm.Quu[q];
-#pragma unroll
-                            for (int i = 0; i < m; i++) f.a[i * m + i] = sm.Quu[i * m + i] + rho * 1.0;
+                            quu_reg(f.a, AB, sm.Quu);
                             BpGroup<C>::lu_factor(f);
                         }
                         ptick(5);
@@ -1593,8 +1623,11 @@ __device__ __forceinline__ void ls_bp_cta_problem(const DevProblem& P, const TOi
                         ptick(6);
                         if (lane <= n) {
                             double rhs[m];
+                            if (lane < n) qux_reg_col(rhs, AB, &sm.Qux[lane * LDm], lane);
+                            else {
 #pragma unroll
-                            for (int i = 0; i < m; i++) rhs[i] = (lane < n) ? sm.Qux[lane * LDm + i] : sm.Qu[i];
+                                for (int i = 0; i < m; i++) rhs[i] = sm.Qu[i];
+                            }
                             BpGroup<C>::lu_solve(f, rhs);
                             if (lane < n) {
                                 double Kc[m];
@@ -1619,10 +1652,7 @@ __device__ __forceinline__ void ls_bp_cta_problem(const DevProblem& P, const TOi
                         __syncwarp();
                         if (lane == 0) {
                             double A_[m * m];
-#pragma unroll
-                            for (int q = 0; q < m * m; q++) A_[q] = sm.QuuC[q];
-#pragma unroll
-                            for (int i = 0; i < m; i++) A_[i * m + i] = sm.QuuC[i * m + i] + rho * 1.0;
+                            quu_reg(A_, AB, sm.QuuC);
                             sm.pd = BpGroup<C>::chol_pd(A_) ? 1 : 0;
                         }
                     }
@@ -1725,14 +1755,14 @@ __device__ __forceinline__ void ls_bp_cta_problem(const DevProblem& P, const TOi
                 // ---- step 3: Quu_reg = Quu + rho*I: PD test (warp 1) beside the LU factorisation and the solves for K, d (warp 0)
                 if (tid <= n) {
                     LU f;
-#pragma unroll
-                    for (int e = 0; e < m * m; e++) f.a[e] = sm.Quu[e];
-#pragma unroll
-                    for (int i = 0; i < m; i++) f.a[i * m + i] = sm.Quu[i * m + i] + rho * 1.0;
+                    quu_reg(f.a, AB, sm.Quu);
                     BpGroup<C>::lu_factor(f);
                     double rhs[m];
+                    if (tid < n) qux_reg_col(rhs, AB, &sm.Qux[tid * LDm], tid);
+                    else {
 #pragma unroll
-                    for (int i = 0; i < m; i++) rhs[i] = (tid < n) ? sm.Qux[tid * LDm + i] : sm.Qu[i];
+                        for (int i = 0; i < m; i++) rhs[i] = sm.Qu[i];
+                    }
                     BpGroup<C>::lu_solve(f, rhs);
                     if (tid < n) {
                         double Kc[m];
@@ -1754,10 +1784,7 @@ __device__ __forceinline__ void ls_bp_cta_problem(const DevProblem& P, const TOi
                     }
                 } else if (tid == 32) {
                     double A_[m * m];
-#pragma unroll
-                    for (int e = 0; e < m * m; e++) A_[e] = sm.Quu[e];
-#pragma unroll
-                    for (int i = 0; i < m; i++) A_[i * m + i] = sm.Quu[i * m + i] + rho * 1.0;
+                    quu_reg(A_, AB, sm.Quu);
                     sm.pd = BpGroup<C>::chol_pd(A_) ? 1 : 0;
                 }
                 __syncthreads();

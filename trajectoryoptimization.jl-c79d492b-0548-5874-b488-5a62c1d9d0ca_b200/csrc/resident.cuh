@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(NT, MINB) ls_resident_kernel(const DevProblem 
     constexpr int NCH = ls_jac_chunks<C, JPC>();
     typedef ResLayout<C, NT> RL;
     static_assert(NT >= 32 * R && NT % 32 == 0, "role warps");
+    static_assert(sizeof(Smem<C>) <= RL::un_bytes, "the warp-level expansion of the :l2 / :linf gradient borrows the phase union");
     extern __shared__ __align__(16) unsigned char res_smem[];
     DevProblem P = Pg;
     ls_stage_problem(P, Pg, res_smem);
