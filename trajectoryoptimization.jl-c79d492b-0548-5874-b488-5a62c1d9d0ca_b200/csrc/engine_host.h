@@ -112,6 +112,7 @@ enum { LS_PHASE_INIT = 0, LS_PHASE_JAC, LS_PHASE_BP, LS_PHASE_TRIAL, LS_PHASE_AC
 struct LsGrids {
     int init, jac, bp, trial, accept, outer;  // grid sizes (persistent, grid-stride)
     int bp_smem, bp_groups_per_block, trial_group;
+    int bp_warps, bp_kernel_smem;  // block shape of ls_bp_kernel itself (bp_smem: the default shape, shared with ls_expand_kernel)
     int occ_jac, occ_bp, occ_trial;
     int jac_pc;  // partial directions per thread in the Jacobian kernel
     int jac_minb, trial_minb, bp_minb, trial_all_minb;

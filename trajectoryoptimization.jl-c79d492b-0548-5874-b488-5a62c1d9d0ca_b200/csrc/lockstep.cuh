@@ -19,6 +19,8 @@
 // arithmetic is identical to the warp-persistent engine (engine.cuh) and to the CPU oracle: the
 // assignment of work to lanes differs, the expression trees do not.
 #pragma once
+#include <cstdio>
+#include <cstdlib>
 #include "engine.cuh"
 #include "sqrt_bp.cuh"
 
@@ -1312,8 +1314,21 @@ struct BpGroup {
     }
 };
 
+template <class C, int WARPS>
+__device__ __forceinline__ void ls_bp_kernel_body(const DevProblem& Pg, const DevCtl& ctl, const LsCtl& lc, const int cur);
+
 template <class C, int WARPS, int MINB>
 __global__ void __launch_bounds__(32 * WARPS, MINB) ls_bp_kernel(const DevProblem Pg, const DevCtl ctl, const LsCtl lc, const int cur) {
+    ls_bp_kernel_body<C, WARPS>(Pg, ctl, lc, cur);
+}
+// the same kernel under an explicit register cap (experiment variants: ptxas rounds a __launch_bounds__ cap of 136 down to 128)
+template <class C, int WARPS, int MAXREG>
+__global__ void __maxnreg__(MAXREG) ls_bp_kernel_mr(const DevProblem Pg, const DevCtl ctl, const LsCtl lc, const int cur) {
+    ls_bp_kernel_body<C, WARPS>(Pg, ctl, lc, cur);
+}
+
+template <class C, int WARPS>
+__device__ __forceinline__ void ls_bp_kernel_body(const DevProblem& Pg, const DevCtl& ctl, const LsCtl& lc, const int cur) {
     constexpr int GS = ls_group_size<C>();
     constexpr int GPB = (32 / GS) * WARPS;  // groups per block
     extern __shared__ __align__(16) unsigned char ls_smem_raw[];
@@ -2522,7 +2537,12 @@ constexpr int LS_TRIAL_G = 8;
 typedef void (*LsJacFn)(const DevProblem, const LsCtl, const int);
 typedef void (*LsTrialFn)(const DevProblem, const DevBatch, const DevCtl, const LsCtl, const int, const int);
 typedef void (*LsBpFn)(const DevProblem, const DevCtl, const LsCtl, const int);
-template <class C> LsBpFn ls_bp_variant(int minb) {
+// Block shape of the lane-group backward pass: 4 warps x 3 blocks per SM at 168 registers.  Measured alternatives on the 65,536
+// quadrotor batch (profiles/r02q_bp_block_shapes.log; bp phase of a step, 3,634 ms for the default): more warps per SM under a
+// register cap all lose to their spills -- 5 warps x 3 blocks at 136 registers 4,814 ms, 3 x 5 at 136: 4,230 ms, 2 x 7 at 144:
+// 4,144 ms, 4 x 4 at 128 (kept as TRAJOPT_B200_BP_MINB=4): 3,700 ms at 16,384 problems vs 3,450.  The kernel wants ~190
+// registers; its latency cannot be hidden by occupancy it does not have room for.
+template <class C> LsBpFn ls_bp_variant(int minb, int warps = LS_BP_WARPS) {
     if constexpr (C::MODEL == 4) {
         if (minb == 4) return ls_bp_kernel<C, LS_BP_WARPS, 4>;
     }
@@ -2571,15 +2591,17 @@ template <class C> unsigned long long ls_ws_doubles_fn(int N, int Ptot) { return
 template <class C> int ls_setup_fn(int sm_count, int N, int nrows, LsGrids* g) {
     constexpr int GPB = (32 / ls_group_size<C>()) * LS_BP_WARPS;
     g->tab_bytes = ls_tab_bytes(N, nrows);
-    g->bp_smem = ls_bp_stride<C>() * GPB + g->tab_bytes;
+    g->bp_smem = ls_bp_stride<C>() * GPB + g->tab_bytes;   // ls_expand_kernel keeps the default block shape
     g->bp_groups_per_block = GPB;
     g->trial_group = LS_TRIAL_G;
     g->bp_minb = 3;
+    g->bp_warps = LS_BP_WARPS;
     if constexpr (C::MODEL == 4) {
         if (const char* env = getenv("TRAJOPT_B200_BP_MINB")) { const int v = atoi(env); if (v == 3 || v == 4) g->bp_minb = v; }
     }
-    if (cudaFuncSetAttribute(ls_bp_variant<C>(g->bp_minb), cudaFuncAttributeMaxDynamicSharedMemorySize, g->bp_smem) != cudaSuccess) return -1;
-    cudaFuncSetAttribute(ls_bp_variant<C>(g->bp_minb), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    g->bp_kernel_smem = ls_bp_stride<C>() * (32 / ls_group_size<C>()) * g->bp_warps + g->tab_bytes;
+    if (cudaFuncSetAttribute(ls_bp_variant<C>(g->bp_minb, g->bp_warps), cudaFuncAttributeMaxDynamicSharedMemorySize, g->bp_kernel_smem) != cudaSuccess) return -1;
+    cudaFuncSetAttribute(ls_bp_variant<C>(g->bp_minb, g->bp_warps), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_init_kernel<C>, 32, 0);
     g->init = sm_count * (nb > 0 ? nb : 1);
@@ -2597,7 +2619,7 @@ template <class C> int ls_setup_fn(int sm_count, int N, int nrows, LsGrids* g) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_jac_variant<C>(g->jac_pc, g->jac_minb), 128, 0);
     g->jac = sm_count * (nb > 0 ? nb : 1);
     g->occ_jac = nb;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_bp_variant<C>(g->bp_minb), 32 * LS_BP_WARPS, g->bp_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_bp_variant<C>(g->bp_minb, g->bp_warps), 32 * g->bp_warps, g->bp_kernel_smem);
     if (nb < 1) return -2;
     g->bp = sm_count * nb;
     g->occ_bp = nb;
@@ -2620,6 +2642,9 @@ template <class C> int ls_setup_fn(int sm_count, int N, int nrows, LsGrids* g) {
     g->res_threads = ls_res_threads<C>();
     g->res_smem = (int)ResLayout<C, ls_res_threads<C>()>::total(N, nrows);
     g->res_minb = 2;
+    // quadrotor: one CTA per SM without a register cap (profiles/r02r: resident phase of the 65,536 batch 1,188 -> 1,046 ms;
+    // half the slots, so the hand-over comes a few ticks later)
+    if constexpr (C::MODEL == 4) g->res_minb = 1;
     if (const char* env = getenv("TRAJOPT_B200_RESIDENT_MINB")) { const int v = atoi(env); if (v == 1 || v == 2) g->res_minb = v; }
     g->res_capacity = 0;
     if (cudaFuncSetAttribute(ls_resident_variant<C>(g->res_minb), cudaFuncAttributeMaxDynamicSharedMemorySize, g->res_smem) == cudaSuccess) {
@@ -2636,7 +2661,7 @@ template <class C> void ls_launch_fn(int phase, const LsGrids& g, cudaStream_t s
     switch (phase) {
         case LS_PHASE_INIT: ls_init_kernel<C><<<g.init, 32, 0, st>>>(P, B, c, lc); break;
         case LS_PHASE_JAC: ls_jac_variant<C>(g.jac_pc, g.jac_minb)<<<g.jac, 128, 0, st>>>(P, lc, cur); break;
-        case LS_PHASE_BP: ls_bp_variant<C>(g.bp_minb)<<<g.bp, 32 * LS_BP_WARPS, g.bp_smem, st>>>(P, c, lc, cur); break;
+        case LS_PHASE_BP: ls_bp_variant<C>(g.bp_minb, g.bp_warps)<<<g.bp, 32 * g.bp_warps, g.bp_kernel_smem, st>>>(P, c, lc, cur); break;
         case LS_PHASE_EXPAND: ls_expand_kernel<C, LS_BP_WARPS><<<grp > 0 ? grp : g.expand, 32 * LS_BP_WARPS, g.bp_smem, st>>>(P, c, lc, cur); break;
         case LS_PHASE_BP_CTA: ls_bp_cta_variant<C>(g.bp_cta_minb)<<<grp > 0 ? grp : g.bp_cta, ls_bp_cta_threads<C>(), g.bp_cta_smem, st>>>(P, c, lc, cur); break;
         case LS_PHASE_BP_SQRT:
