@@ -66,3 +66,15 @@ def test_trim_entry_follows_the_reference_logger():
     assert _trim_entry(-3.5, 10) == "-3.5".ljust(10)
     assert _trim_entry(1.0e-9, 10).strip() == "1e-09" and _trim_entry(12, 6) == "12".ljust(6)
     assert _trim_entry(float("inf"), 10).strip() == "Inf"
+
+
+def test_time_validation_follows_the_reference():
+    # src/problem.jl:169-220 (and test/problem_tests.jl:53-55,77-80: dt == 0.3 from tf, N; disagreement throws)
+    from trajopt_b200.api import _validate_time
+    nan = float("nan")
+    assert _validate_time(11, 3.0, nan) == (11, 3.0, 0.3)
+    assert _validate_time(21, nan, 0.05) == (21, 0.05 * 20, 0.05)
+    assert _validate_time(21, 0.0, 0.1) == (21, 0.0, 0.1)                  # minimum time keeps the initial dt
+    for args in ((11, 3.0, 0.25), (11, nan, nan), (11, nan, -0.1), (11, 0.0, nan), (11, -1.0, 0.1)):
+        with pytest.raises(ValueError):
+            _validate_time(*args)

@@ -255,20 +255,32 @@ class Problem:
 
 
 def _validate_time(N, tf, dt):
-    """src/problem.jl:169-220 (the cases the fixtures use)."""
+    """_validate_time (src/problem.jl:169-220).  N is always known here (the objective carries one cost per knot), so the
+    reference's N == -1 branches do not arise; the error cases are the reference's ArgumentErrors."""
     has_dt, has_tf = not math.isnan(dt), not math.isnan(tf)
-    if has_tf and tf == 0.0:  # minimum time
+    if not has_dt and not has_tf:
+        raise ValueError("Must specify at least 2: N, dt, or tf")
+    if has_tf and tf == 0.0:  # minimum time (tf == 0 or :min): dt is the initial time step
         if not has_dt:
             raise ValueError("minimum-time problems need an initial dt")
-        return N, 0.0, dt
-    if has_dt and has_tf:
-        N = int(round(tf / dt)) + 1
-        return N, tf, dt
-    if has_dt:
-        return N, dt * (N - 1), dt
-    if has_tf:
-        return N, tf, tf / (N - 1)
-    raise ValueError("at least one of dt, tf must be given")
+    elif has_tf and tf > 0:
+        if not has_dt:
+            dt = tf / (N - 1)
+        elif dt != tf / (N - 1):
+            raise ValueError("Specified time step, number of knot points, and final time do not agree (%r != %r/%d)" % (dt, tf, N - 1))
+        if dt == 0:
+            raise ValueError("dt must be non-zero for non-minimum time problems")
+    elif not has_tf:
+        if not dt > 0:
+            raise ValueError("dt must be positive for a non-minimum-time problem")
+        tf = dt * (N - 1)
+    else:
+        raise ValueError("Invalid input for tf")
+    if N < 0:
+        raise ValueError("%d is not a valid entry for N. Number of knot points must be a positive integer." % N)
+    if dt < 0:
+        raise ValueError("%r is not a valid entry for dt. Time step must be positive." % dt)
+    return N, tf, dt
 
 
 def initial_controls_b(prob, U0):

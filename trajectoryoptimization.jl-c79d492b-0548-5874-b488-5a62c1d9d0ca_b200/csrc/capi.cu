@@ -18,7 +18,7 @@ using namespace tob;
 
 namespace {
 
-std::string g_create_error;
+thread_local std::string g_create_error;  // per thread: to_create may be called from several host threads (one handle each)
 
 #define CK_RET(s, call)                                                                            \
     do {                                                                                           \
@@ -344,8 +344,16 @@ int ensure_engine_buffers(TOSolver* s, Variant& v) {
         return s->fail(TO_ERR_NOMEM, buf);
     }
     if (cudaMalloc(&v.lc.st, B * sizeof(LsState)) != cudaSuccess || cudaMalloc(&v.ls_lists, 6 * B * sizeof(int)) != cudaSuccess ||
-        cudaMalloc(&v.lc.counts, 64) != cudaSuccess)
+        cudaMalloc(&v.lc.counts, 64) != cudaSuccess) {
+        cudaGetLastError();
+        const bool built = v.built;  // keep the problem tables, drop the partly allocated workspaces
+        std::vector<void*> keep;
+        keep.swap(v.allocs);
+        free_variant(v);
+        v.allocs.swap(keep);
+        v.built = built;
         return s->fail(TO_ERR_NOMEM, "cudaMalloc failed (lockstep state)");
+    }
     v.lc.list[0] = v.ls_lists; v.lc.list[1] = v.ls_lists + B;
     v.lc.retry[0] = v.ls_lists + 2 * B; v.lc.retry[1] = v.ls_lists + 3 * B;
     v.lc.outer_list = v.ls_lists + 4 * B;
@@ -813,6 +821,15 @@ int to_create(const TOProblemDesc* desc, int32_t B, int32_t device, TOHandle* ou
     if (desc->n != mn || desc->m != mm) return fail_create(TO_ERR_INVALID, "n/m do not match the model");
     if (desc->N < 2) return fail_create(TO_ERR_INVALID, "N must be >= 2");
     if (!(desc->dt > 0)) return fail_create(TO_ERR_INVALID, "dt must be strictly positive");  // problem.jl:66-68
+    if (!desc->Q || !desc->R || !desc->q || !desc->r || !desc->Qf || !desc->qf)
+        return fail_create(TO_ERR_INVALID, "to_create: Q, R, q, r, Qf, qf must not be NULL (only H may be)");
+    if (desc->n_classes > 0) {
+        if (!desc->class_of_knot || !desc->class_row_start) return fail_create(TO_ERR_INVALID, "to_create: class tables must not be NULL");
+        if (desc->class_row_start[0] != 0) return fail_create(TO_ERR_INVALID, "class_row_start must begin at 0");
+        for (int c = 0; c < desc->n_classes; c++)
+            if (desc->class_row_start[c + 1] < desc->class_row_start[c]) return fail_create(TO_ERR_INVALID, "class_row_start must be non-decreasing");
+        if (desc->class_row_start[desc->n_classes] > 0 && !desc->rows) return fail_create(TO_ERR_INVALID, "to_create: rows must not be NULL");
+    }
     if (!find_kernel(desc->model, desc->integrator, 0, 0)) return fail_create(TO_ERR_UNSUPPORTED, "no kernel for this model/integrator");
     int ndev = to_device_count();
     if (ndev <= 0) return fail_create(TO_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
