@@ -192,6 +192,13 @@ def _dp_sqrt_ilqr(B):
     return p, api.iLQRSolverOptions(square_root=True), problems.batch_x0("doublependulum", B), None
 
 
+def _quad_sqrt_ilqr(B):
+    """the square-root pass on the largest model (n = 13, m = 4): unconstrained quadrotor iLQR"""
+    p = problems.quadrotor()
+    p.constraints = api.Constraints(p.N)
+    return p, api.iLQRSolverOptions(square_root=True, iterations=40), problems.batch_x0("quadrotor", B), None
+
+
 def _acrobot_sqrt_al(B):
     p = problems.acrobot()
     x0 = problems.batch_x0("acrobot", B)
@@ -242,6 +249,7 @@ CASES = {
     "pend_sqrt_altro": _pend_sqrt_altro,
     "dp_sqrt_ilqr": _dp_sqrt_ilqr,
     "acrobot_sqrt_al": _acrobot_sqrt_al,
+    "quad_sqrt_ilqr": _quad_sqrt_ilqr,
     "acrobot_sqrt_mintime": _sqrt_mintime("acrobot"),
     "dp_sqrt_mintime": _sqrt_mintime("doublependulum"),
 }

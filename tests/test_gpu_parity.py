@@ -132,6 +132,27 @@ def test_backward_pass_kernels_agree_bitwise(to, monkeypatch):
         assert np.array_equal(a["X"], other["X"], equal_nan=True) and np.array_equal(a["U"], other["U"], equal_nan=True)
 
 
+@pytest.mark.parametrize("name", ["pend_sqrt_altro", "dp_sqrt_ilqr", "acrobot_sqrt_al", "quad_sqrt_ilqr", "acrobot_sqrt_mintime",
+                                  "dp_sqrt_mintime"])
+def test_square_root_pass_kernels_agree_bitwise(to, oracle, name, monkeypatch):
+    """the two kernels of the square-root backward pass (sqrt_bp.cuh): thread per problem (full batches, and the small models at
+    any size) and warp per problem (few live problems of a model too large for one thread's registers) -- the same records, X and
+    U bit for bit, and both equal to the oracle"""
+    B = 8
+    prob, opts, x0, X0 = CASES[name](B)
+    ref = oracle.solve(prob, opts, x0=x0, X0=X0, B=B, inner_cap=2048, outer_cap=96)
+    monkeypatch.setenv("TRAJOPT_B200_SQRT_WARP_THRESHOLD", "1000000")
+    warp = _solve_gpu(to, prob, opts, x0, X0, B)
+    monkeypatch.setenv("TRAJOPT_B200_SQRT_WARP_THRESHOLD", "0")
+    thread = _solve_gpu(to, prob, opts, x0, X0, B)
+    assert warp["results"].tobytes() == thread["results"].tobytes()
+    assert np.array_equal(warp["X"], thread["X"], equal_nan=True) and np.array_equal(warp["U"], thread["U"], equal_nan=True)
+    for b in range(B):
+        for f in ("cost", "dJ", "gradient", "expected", "z", "rho", "alpha"):
+            assert np.array_equal(warp["inner"][b][f], thread["inner"][b][f], equal_nan=True), (b, f)
+    _compare(ref, thread, B)
+
+
 @pytest.mark.parametrize("name", ["di_altro", "quad_altro", "quad_regdiv", "cart_ilqr", "escape_notebook", "park_inf_altro", "pend_mintime"])
 def test_parity_persistent_engine(to, oracle, name, monkeypatch):
     """the second, independent CUDA implementation (one warp-resident kernel per solve, engine.cuh) against the same oracle"""

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One parameterised GPU round (replaces the per-experiment gpu_round_*.sh scripts).
-#   tools/gpu_round.sh TAG step [step...]      steps: test smoke bench bench16k ref configs ncu_launches ncu_full ticks16k
+#   tools/gpu_round.sh TAG step [step...]      steps: test testk=EXPR smoke bench bench16k ref configs cfg=CASE ncu_launches ncu_full ticks16k env=VAR=VALUE tag=TAG
 # Everything lands in gpurun_out/TAG_*.  Bench numbers are never taken under ncu.
 TAG=$1; shift
 OUT=gpurun_out
@@ -40,6 +40,9 @@ for step in "$@"; do
             timeout 900 ncu --set full --clock-control none --import-source on -k regex:'ls_resident_kernel' -c 1 -f -o $OUT/${TAG}_prof_resident \
                 python tools/resident_profile.py quad_altro 8 > $OUT/${TAG}_ncu_resident.log 2>&1
             echo "ncu resident exit $?" ;;
+    cfg=*)  CNAME="${step#cfg=}"; TRAJOPT_B200_TICK_LOG=$OUT/${TAG}_ticks_${CNAME}.txt TRAJOPT_B200_TICK_DETAIL=1 timeout 900 python tools/run_configs.py ${TAG}_${CNAME} 1 $CNAME > $OUT/${TAG}_cfg_${CNAME}.log 2>&1
+            echo "config $CNAME exit $?"; tail -2 $OUT/${TAG}_cfg_${CNAME}.log | cut -c1-500; tail -4 $OUT/${TAG}_ticks_${CNAME}.txt ;;
+    sqrttime) timeout 600 python tools/sqrt_pass_timing.py 8 > $OUT/${TAG}_sqrt_pass_timing.log 2>&1; echo "sqrttime exit $?"; cat $OUT/${TAG}_sqrt_pass_timing.log ;;
     bpprof) timeout 300 python tools/bp_profile.py 8192 > $OUT/${TAG}_bp_profile.log 2>&1; echo "bpprof exit $?"; cat $OUT/${TAG}_bp_profile.log ;;
     env=*)  export "${step#env=}" ;;
     tag=*)  TAG="${step#tag=}" ;;

@@ -28,6 +28,9 @@ CONFIGS = [
     ("configs[3] parallel_park infeasible ALTRO", "park_inf_altro", 16384, 8),
     ("configs[4] acrobot sqrt + min-time ALTRO", "acrobot_sqrt_mintime", 32768, 8),
     ("configs[4] doublependulum sqrt + min-time ALTRO", "dp_sqrt_mintime", 32768, 8),
+    # configs[4] ends NOT_PD_SQRT for almost every problem (faithful to the reference): the square-root pass on a batch
+    # that runs to convergence is measured on the fixed-time acrobot instead
+    ("square-root pass, non-degenerate: acrobot sqrt AL, fixed time", "acrobot_sqrt_al", 32768, 8),
 ]
 
 

@@ -450,6 +450,12 @@ int run_lockstep_impl(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl&
     int inline_restarts = LS_BP_INLINE_RESTARTS;
     if (const char* env = getenv("TRAJOPT_B200_BP_INLINE_RESTARTS")) inline_restarts = std::max(0, std::min(64, atoi(env)));
     if (const char* env = getenv("TRAJOPT_B200_BP_CTA_THRESHOLD")) cta_threshold = (unsigned int)strtoul(env, nullptr, 10);
+    // square-root pass: warp per problem once the live problems fit one wave of warps (sqrt_bp.cuh) -- for the models whose
+    // matrices do not fit the registers of one thread (measured, profiles/r02x_sqrt_pass_timing.log: quadrotor 9.6x faster than
+    // thread per problem, whose frame is local memory; the small models keep everything in registers and are 1.4-1.6x SLOWER
+    // through shared memory, so they stay on the thread kernel)
+    unsigned int sqrt_warp_threshold = (v.ki->n > 6 || v.ki->m > 6) ? (unsigned int)s->sm_count * 16u : 0u;
+    if (const char* env = getenv("TRAJOPT_B200_SQRT_WARP_THRESHOLD")) sqrt_warp_threshold = (unsigned int)strtoul(env, nullptr, 10);
     // diagnostics: TRAJOPT_B200_TICK_LOG=<file> records one event per tick and writes "tick ms active" lines
     const char* tick_log = getenv("TRAJOPT_B200_TICK_LOG");
     const bool collect = tick_log || s->phase_timing;  // one CUDA event per phase (or per tick) on the solve stream
@@ -554,7 +560,8 @@ int run_lockstep_impl(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl&
             v.ki->ls_launch(LS_PHASE_BP_CTA, v.grids, st, v.P, Bt, c, v.lc, cur, (int)std::min<unsigned int>(known_active, (unsigned int)v.grids.bp_cta));
             s->launches += 1;
         } else if (c.o.opts_uncon.square_root) {
-            v.ki->ls_launch(LS_PHASE_BP_SQRT, v.grids, st, v.P, Bt, c, v.lc, cur, 0);
+            // thread per problem while the batch fills the machine, warp per problem (same bits, a shorter chain) below that
+            v.ki->ls_launch(LS_PHASE_BP_SQRT, v.grids, st, v.P, Bt, c, v.lc, cur, (known_active <= sqrt_warp_threshold) ? (int)known_active : 0);
         } else if (defer_restarts) {
             // bulk: the lane-group kernel serves up to LS_BP_INLINE_RESTARTS regularisation increases per problem itself and
             // queues the rare long restart chains (restart list, zeroed by the Jacobian kernel) for the latency path

@@ -2666,7 +2666,8 @@ template <class C> void ls_launch_fn(int phase, const LsGrids& g, cudaStream_t s
         case LS_PHASE_BP_CTA: ls_bp_cta_variant<C>(g.bp_cta_minb)<<<grp > 0 ? grp : g.bp_cta, ls_bp_cta_threads<C>(), g.bp_cta_smem, st>>>(P, c, lc, cur); break;
         case LS_PHASE_BP_SQRT:
             ls_expand_sqrt_kernel<C><<<g.jac, 64, 0, st>>>(P, c, lc, cur);
-            ls_bp_sqrt_kernel<C><<<g.accept, 64, 0, st>>>(P, c, lc, cur);
+            if (grp > 0) ls_bp_sqrt_warp_kernel<C><<<grp, 32, 0, st>>>(P, c, lc, cur);   // few live problems: warp per problem
+            else ls_bp_sqrt_kernel<C><<<g.accept, 64, 0, st>>>(P, c, lc, cur);
             break;
         case LS_PHASE_TRIAL: ls_trial_variant<C>(g.trial_minb, false)<<<g.trial, 128, g.tab_bytes, st>>>(P, B, c, lc, cur, grp); break;
         case LS_PHASE_TRIAL_ALL: ls_trial_variant<C>(g.trial_all_minb, true)<<<g.trial, 128, g.tab_bytes, st>>>(P, B, c, lc, cur, 0); break;

@@ -2,11 +2,12 @@
 // augmented_lagrangian_methods.jl:231-276): the cost-to-go and the action-value Hessians are carried as
 // upper-triangular factors, updated with QR "up-dates" (chol_plus) and rank-one down-dates (chol_minus).
 //
-// One THREAD per problem: the factor updates are chains of small Householder reflections with data-dependent
-// branches (cond() by one-sided Jacobi, PosDefException exits), i.e. serial per problem, and the path exists
-// for ill-conditioned small systems (BASELINE config 5: n <= 5), not for throughput.  All matrices are
-// column-major thread-local arrays of compile-time size; every loop follows the order of the CPU restatement
-// so the results are bit-identical to it.
+// Two kernels with identical results.  One THREAD per problem (SqrtBp): the factor updates are chains of small Householder
+// reflections with data-dependent branches (cond() by one-sided Jacobi, PosDefException exits), i.e. serial per problem; all
+// matrices are column-major thread-local arrays of compile-time size, which the compiler keeps in registers for the small
+// models (BASELINE config 5: n <= 5).  One WARP per problem (SqrtWarp, further down): matrices in shared memory, one lane per
+// output element -- for the models whose matrices would be a local-memory frame (quadrotor: 22 KB) when few problems are live.
+// Every output follows the operation order of the CPU restatement in both, so the results are bit-identical to it.
 #pragma once
 #include "engine.cuh"
 
@@ -535,6 +536,343 @@ __global__ void __launch_bounds__(64) ls_bp_sqrt_kernel(const DevProblem P, cons
         st->rho = rho; st->drho = drho; st->dV0 = dV0; st->dV1 = dV1;
         st->winner = -1;
         st->bp_fail = rc;
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Latency form of the same recursion: one WARP per problem, every matrix in shared memory, one lane per OUTPUT element.
+// Each output is still produced by the sequential chain of SqrtBp::run (same operands, same order), so the two kernels agree bit
+// for bit; what changes is that independent outputs -- the columns a Householder reflection updates, the right-hand sides of a
+// triangular solve, the entries of a product, the two factor updates of a knot -- run side by side instead of one after the other,
+// and that no matrix lives in a thread-local frame.  The rank-one down-dates (n rows against the m×m factor, backward_pass.jl:165-170)
+// run as a pipeline: lane i owns pivot row i and hands the modified row vector to lane i+1.
+template <class C>
+struct SqrtWarpSmem {
+    static constexpr int n = C::n, m = C::m;
+    static constexpr int RB = (n > m) ? n : m;
+    double Sxx[n * n], Sx[n], SxxN[n * n], SxN[n];
+    double A[n * n], Bm[n * m];
+    double Q[C::QS];
+    double tx[n * n], tu[n * m];
+    double P1[(n + RB) * n];      // stacked matrix of the n-column factor updates (rows: 2n, then n+m)
+    double P2[(m + RB) * m];      // stacked matrix of the m-column factor updates (rows: m+n, then 2m)
+    double Qreg[m * m];
+    double K[m * n], d[m];
+    double KQt[n * m], Qd[m], v2[n], v3[n], Sxk[n];
+    double tmp1[n * m], U2[m * m];
+};
+
+template <class C>
+struct SqrtWarp {
+    static constexpr int n = C::n, m = C::m;
+
+    // Householder QR (same reflections as SqrtBp::qr_R) of two stacked matrices at once: lanes 0-15 work on P1 (rows1 × D1),
+    // lanes 16-31 on P2 (rows2 × D2).  Every lane of a half computes the column norm itself (a sequential chain that cannot be
+    // split); the reflection is then applied to one column per lane.  The scaled Householder vector is never stored: only R is
+    // read afterwards.
+    static __device__ __forceinline__ void qr_pair(double* P1, int rows1, int D1, double* P2, int rows2, int D2, int lane) {
+        const int half = lane >> 4, gl = lane & 15;
+        double* Pm = half ? P2 : P1;
+        const int rows = half ? rows2 : rows1, D = half ? D2 : D1;
+        const int DM = (D1 > D2) ? D1 : D2;
+        for (int j = 0; j < DM; j++) {
+            const bool on = (j < D && j < rows);
+            double tau = 0.0, sc = 0.0, beta = 0.0;
+            bool refl = false;
+            if (on) {
+                const double* cj = Pm + j * rows;
+                const double alpha = cj[j];
+                double xn2 = 0.0;
+                for (int i = j + 1; i < rows; i++) xn2 = fma(cj[i], cj[i], xn2);
+                if (xn2 != 0.0) {
+                    const double xnorm = sqrt(xn2);
+                    beta = -copysign(sqrt(alpha * alpha + xnorm * xnorm), alpha);
+                    tau = (beta - alpha) / beta;
+                    sc = 1.0 / (alpha - beta);
+                    refl = true;
+                }
+            }
+            // (column j is only read from here on, columns c > j are each written by their own lane: no barrier needed yet)
+            if (on && tau != 0.0) {
+                const double* cj = Pm + j * rows;
+                for (int c = j + 1 + gl; c < D; c += 16) {
+                    double* cc = Pm + c * rows;
+                    double w = cc[j];
+                    for (int i = j + 1; i < rows; i++) w = fma(cj[i] * sc, cc[i], w);
+                    const double tw = tau * w;
+                    cc[j] = cc[j] - tw;
+                    for (int i = j + 1; i < rows; i++) cc[i] = fma(-tw, cj[i] * sc, cc[i]);
+                }
+            }
+            __syncwarp();
+            // (the diagonal entry is written once every lane is past the reads of column j)
+            if (refl && gl == 0) Pm[j * rows + j] = beta;
+        }
+        __syncwarp();
+    }
+
+    static __device__ int run(const DevProblem& P, const TOiLQROptions& io, double* ws, const WsLayout& L, SqrtWarpSmem<C>& sm,
+                              const int lane, double& rho, double& drho, double& dV0, double& dV1) {
+        const int N = P.N;
+        double* qst = ws + L.QST;
+        {
+            const double* E = qst + (size_t)(N - 1) * C::QS;
+            for (int e = lane; e < n * n; e += 32) { const double v = E[n + m + e]; sm.Sxx[e] = v; sm.SxxN[e] = v; }
+            for (int i = lane; i < n; i += 32) { const double v = E[i]; sm.Sx[i] = v; sm.SxN[i] = v; }
+        }
+        dV0 = 0.0;
+        dV1 = 0.0;
+        double* Qx = sm.Q;
+        double* Qu = sm.Q + n;
+        double* Qxx = sm.Q + n + m;
+        double* Quu = Qxx + n * n;
+        double* Qux = Quu + m * m;
+        int k = N - 2;
+        while (k >= 0) {
+            __syncwarp();
+            {
+                const double* ab = ws + L.Z + (size_t)k * C::ZA;
+                for (int e = lane; e < n * n; e += 32) { const int jj = e / n, i = e - jj * n; sm.A[e] = ab[i * C::LDZ + jj]; }
+                for (int e = lane; e < n * m; e += 32) { const int jj = e / n, i = e - jj * n; sm.Bm[e] = ab[i * C::LDZ + n + jj]; }
+                const double* Qg = qst + (size_t)k * C::QS;
+                for (int e = lane; e < C::QS; e += 32) sm.Q[e] = Qg[e];
+            }
+            __syncwarp();
+            // Sxx*A, Sxx*B, A'Sx, B'Sx: one output per lane
+            for (int e = lane; e < n * n + n * m + n + m; e += 32) {
+                double acc = 0.0;
+                if (e < n * n) {
+                    const int j = e / n, i = e - j * n;
+                    for (int l = 0; l < n; l++) acc = fma(sm.Sxx[l * n + i], sm.A[j * n + l], acc);
+                    sm.tx[e] = acc;
+                } else if (e < n * n + n * m) {
+                    const int f = e - n * n, j = f / n, i = f - j * n;
+                    for (int l = 0; l < n; l++) acc = fma(sm.Sxx[l * n + i], sm.Bm[j * n + l], acc);
+                    sm.tu[f] = acc;
+                } else if (e < n * n + n * m + n) {
+                    const int i = e - n * n - n * m;
+                    for (int l = 0; l < n; l++) acc = fma(sm.A[i * n + l], sm.Sx[l], acc);
+                    Qx[i] += acc;
+                } else {
+                    const int i = e - n * n - n * m - n;
+                    for (int l = 0; l < n; l++) acc = fma(sm.Bm[i * n + l], sm.Sx[l], acc);
+                    Qu[i] += acc;
+                }
+            }
+            __syncwarp();
+            // [Qxx; Sxx A] and [Quu; Sxx B] stacked; Qux += (Sxx B)'(Sxx A)
+            for (int e = lane; e < 2 * n * n; e += 32) {
+                const int j = e / (2 * n), i = e - j * 2 * n;
+                sm.P1[e] = (i < n) ? Qxx[j * n + i] : sm.tx[j * n + (i - n)];
+            }
+            for (int e = lane; e < (m + n) * m; e += 32) {
+                const int j = e / (m + n), i = e - j * (m + n);
+                sm.P2[e] = (i < m) ? Quu[j * m + i] : sm.tu[j * n + (i - m)];
+            }
+            for (int e = lane; e < m * n; e += 32) {
+                const int j = e / m, i = e - j * m;
+                double acc = 0.0;
+                for (int l = 0; l < n; l++) acc = fma(sm.tu[i * n + l], sm.tx[j * n + l], acc);
+                Qux[e] += acc;
+            }
+            __syncwarp();
+            qr_pair(sm.P1, 2 * n, n, sm.P2, m + n, m, lane);
+            {
+                double* Qg = qst + (size_t)k * C::QS;
+                for (int e = lane; e < n * n; e += 32) { const int j = e / n, i = e - j * n; Qxx[e] = (i <= j) ? sm.P1[j * 2 * n + i] : 0.0; }
+                for (int e = lane; e < m * m; e += 32) { const int j = e / m, i = e - j * m; Quu[e] = (i <= j) ? sm.P2[j * (m + n) + i] : 0.0; }
+                __syncwarp();
+                // written back before the regularisation test: a restart finds the accumulated values (quirk Q1)
+                for (int e = lane; e < C::QS; e += 32) Qg[e] = sm.Q[e];
+            }
+            // Quu_reg = chol_plus(Quu, sqrt(rho) I)
+            const double sr = sqrt(rho);
+            for (int e = lane; e < 2 * m * m; e += 32) {
+                const int j = e / (2 * m), i = e - j * 2 * m;
+                sm.P2[e] = (i < m) ? Quu[j * m + i] : ((i - m == j) ? sr * 1.0 : 0.0);
+            }
+            __syncwarp();
+            qr_pair(sm.P2, 2 * m, m, sm.P2, 0, 0, lane);
+            for (int e = lane; e < m * m; e += 32) { const int j = e / m, i = e - j * m; sm.Qreg[e] = (i <= j) ? sm.P2[j * 2 * m + i] : 0.0; }
+            __syncwarp();
+            // (every lane runs the Jacobi sweeps on its own register copy: a chain with nothing to share out)
+            if (SqrtBp<C>::template cond2<m, 64>(sm.Qreg) > 1e8) {
+                if (!isfinite(rho)) return 1;
+                const double f = io.bp_reg_increase_factor;  // regularization_update!(:increase)
+                drho = dmax(drho * f, f);
+                rho = dmax(rho * drho, io.bp_reg_min);
+                k = N - 2;
+                __syncwarp();
+                for (int e = lane; e < n * n; e += 32) sm.Sxx[e] = sm.SxxN[e];
+                for (int i = lane; i < n; i += 32) sm.Sx[i] = sm.SxN[i];
+                dV0 = 0.0;
+                dV1 = 0.0;
+                continue;
+            }
+            // K = -Quu_reg \ (Quu_reg' \ Qux), d likewise: one right-hand side per lane
+            for (int c = lane; c < n + 1; c += 32) {
+                double t1[m], x2[m];
+#pragma unroll
+                for (int i = 0; i < m; i++) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < i; l++) acc = fma(sm.Qreg[i * m + l], t1[l], acc);
+                    const double rhs = (c < n) ? Qux[c * m + i] : Qu[i];
+                    t1[i] = (rhs - acc) / sm.Qreg[i * m + i];
+                }
+#pragma unroll
+                for (int i = m - 1; i >= 0; i--) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int l = i + 1; l < m; l++) acc = fma(sm.Qreg[l * m + i], x2[l], acc);
+                    x2[i] = (t1[i] - acc) / sm.Qreg[i * m + i];
+                }
+                double* kd = ws + L.KD + (size_t)k * C::KDS;
+#pragma unroll
+                for (int i = 0; i < m; i++) {
+                    const double v = -x2[i];
+                    if (c < n) { sm.K[c * m + i] = v; kd[c * m + i] = v; }
+                    else { sm.d[i] = v; kd[m * n + i] = v; }
+                }
+            }
+            __syncwarp();
+            // K'Quu', Quu d, K'Qu, Qux'd, and (Qxx') \ Qux' (one column per lane, taken by the last lanes)
+            for (int e = lane; e < n * m + m + n + n; e += 32) {
+                double acc = 0.0;
+                if (e < n * m) {
+                    const int jj = e / n, i = e - jj * n;
+                    for (int l = 0; l < m; l++) acc = fma(sm.K[i * m + l], Quu[l * m + jj], acc);
+                    sm.KQt[e] = acc;
+                } else if (e < n * m + m) {
+                    const int i = e - n * m;
+                    for (int l = 0; l < m; l++) acc = fma(Quu[l * m + i], sm.d[l], acc);
+                    sm.Qd[i] = acc;
+                } else if (e < n * m + m + n) {
+                    const int i = e - n * m - m;
+                    for (int l = 0; l < m; l++) acc = fma(sm.K[i * m + l], Qu[l], acc);
+                    sm.v2[i] = acc;
+                } else {
+                    const int i = e - n * m - m - n;
+                    for (int l = 0; l < m; l++) acc = fma(Qux[i * m + l], sm.d[l], acc);
+                    sm.v3[i] = acc;
+                }
+            }
+            for (int c = 31 - lane; c < m; c += 32) {
+                for (int i = 0; i < n; i++) {
+                    double acc = 0.0;
+                    for (int l = 0; l < i; l++) acc = fma(Qxx[i * n + l], sm.tmp1[c * n + l], acc);
+                    sm.tmp1[c * n + i] = (Qux[i * m + c] - acc) / Qxx[i * n + i];
+                }
+            }
+            for (int e = lane; e < m * m; e += 32) sm.U2[e] = Quu[e];
+            __syncwarp();
+            // S.x = Q.x + (K'Quu')(Quu d) + K'Qu + Qux'd ; expected change
+            for (int i = lane; i < n; i += 32) {
+                double acc = 0.0;
+                for (int l = 0; l < m; l++) acc = fma(sm.KQt[l * n + i], sm.Qd[l], acc);
+                sm.Sxk[i] = ((Qx[i] + acc) + sm.v2[i]) + sm.v3[i];
+            }
+            // tmp2 = chol_minus(Q.uu, tmp1): n rank-one down-dates, pipelined over the pivot rows (lane i = pivot i)
+            {
+                double Urow[m], vv[m];
+#pragma unroll
+                for (int j = 0; j < m; j++) { Urow[j] = (lane < m && j >= lane) ? sm.U2[j * m + lane] : 0.0; vv[j] = 0.0; }
+                bool bad = false;
+                for (int t = 0; t < n + m - 1; t++) {
+#pragma unroll
+                    for (int j = 0; j < m; j++) {
+                        const double up = __shfl_up_sync(FULL, vv[j], 1);
+                        if (lane > 0) vv[j] = up;
+                    }
+                    if (lane == 0 && t < n) {
+#pragma unroll
+                        for (int j = 0; j < m; j++) vv[j] = sm.tmp1[j * n + t];
+                    }
+                    const int r = t - lane;
+                    if (lane < m && r >= 0 && r < n) {
+                        double Aii = 0.0, vi = 0.0;
+#pragma unroll
+                        for (int j = 0; j < m; j++) if (j == lane) { Aii = Urow[j]; vi = vv[j]; }
+                        const double s = vi / Aii;
+                        const double s2 = s * s;
+                        if (s2 > 1.0) bad = true;
+                        const double c = sqrt(1.0 - s2);
+#pragma unroll
+                        for (int j = 0; j < m; j++) {
+                            if (j == lane) {
+                                Urow[j] = c * Aii;
+                            } else if (j > lane) {
+                                const double vj = vv[j];
+                                const double Aij = (Urow[j] - s * vj) / c;
+                                Urow[j] = Aij;
+                                vv[j] = -s * Aij + c * vj;
+                            }
+                        }
+                    }
+                }
+                if (__any_sync(FULL, bad)) return 2;
+                double a = 0.0;
+                for (int l = 0; l < m; l++) a = fma(sm.d[l], Qu[l], a);
+                dV0 += a;
+                double b = 0.0;
+                for (int l = 0; l < m; l++) b = fma(sm.Qd[l], sm.Qd[l], b);
+                dV1 += 0.5 * b;
+                if (lane < m) {
+#pragma unroll
+                    for (int j = 0; j < m; j++) if (j >= lane) sm.U2[j * m + lane] = Urow[j];
+                }
+            }
+            __syncwarp();
+            // S.xx = chol_plus(Q.xx + tmp1*K, tmp2*K)
+            for (int e = lane; e < n * n + m * n; e += 32) {
+                double acc = 0.0;
+                if (e < n * n) {
+                    const int j = e / n, i = e - j * n;
+                    for (int l = 0; l < m; l++) acc = fma(sm.tmp1[l * n + i], sm.K[j * m + l], acc);
+                    sm.P1[j * (n + m) + i] = Qxx[e] + acc;
+                } else {
+                    const int f = e - n * n, j = f / m, i = f - j * m;
+                    for (int l = 0; l < m; l++) acc = fma(sm.U2[l * m + i], sm.K[j * m + l], acc);
+                    sm.P1[j * (n + m) + n + i] = acc;
+                }
+            }
+            __syncwarp();
+            qr_pair(sm.P1, n + m, n, sm.P1, 0, 0, lane);
+            for (int e = lane; e < n * n; e += 32) { const int j = e / n, i = e - j * n; sm.Sxx[e] = (i <= j) ? sm.P1[j * (n + m) + i] : 0.0; }
+            for (int i = lane; i < n; i += 32) sm.Sx[i] = sm.Sxk[i];
+            k--;
+        }
+        {
+            const double f = io.bp_reg_increase_factor;  // regularization_update!(:decrease)
+            drho = dmin(drho / f, 1.0 / f);
+            rho = rho * drho * ((rho * drho > io.bp_reg_min) ? 1.0 : 0.0);
+        }
+        return 0;
+    }
+};
+
+// warp per problem (few live problems: the pass is a latency chain)
+template <class C>
+__global__ void __launch_bounds__(32) ls_bp_sqrt_warp_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
+    __shared__ SqrtWarpSmem<C> sm;
+    const unsigned int na = lc.counts[cur];
+    const WsLayout L = ws_layout<C>(P.N, P.Ptot, false);
+    const int lane = threadIdx.x;
+    for (unsigned int a = blockIdx.x; a < na; a += gridDim.x) {
+        const int b = lc.list[cur][a];
+        LsState* st = &lc.st[b];
+        const TOiLQROptions& io = ctl.o.opts_uncon;
+        double rho = st->rho, drho = st->drho, dV0 = 0.0, dV1 = 0.0;
+        const int pre = st->bp_fail;
+        __syncwarp();
+        const int rc = (pre == 2) ? 2 : SqrtWarp<C>::run(P, io, lc.ws + (size_t)b * lc.ws_stride, L, sm, lane, rho, drho, dV0, dV1);
+        __syncwarp();
+        if (lane == 0) {
+            st->rho = rho; st->drho = drho; st->dV0 = dV0; st->dV1 = dV1;
+            st->winner = -1;
+            st->bp_fail = rc;
+        }
     }
 }
 
