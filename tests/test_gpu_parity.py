@@ -132,6 +132,26 @@ def test_backward_pass_kernels_agree_bitwise(to, monkeypatch):
         assert np.array_equal(a["X"], other["X"], equal_nan=True) and np.array_equal(a["U"], other["U"], equal_nan=True)
 
 
+def test_split_line_search_agrees_bitwise(to, oracle, monkeypatch):
+    """car_escape (177 constraint rows per knot) on the lockstep tick in tail mode: the cost evaluated ON the state chain (one
+    kernel) and OFF it (chains, then the costs of all (knot, step size), then the pick; resident.cuh) -- identical records, X, U and
+    iteration traces, and equal to the oracle"""
+    monkeypatch.setenv("TRAJOPT_B200_RESIDENT_THRESHOLD", "0")
+    B = 4
+    prob, opts, x0, X0 = CASES["escape_notebook"](B)
+    ref = oracle.solve(prob, opts, x0=x0, X0=X0, B=B, inner_cap=2048, outer_cap=96)
+    split = _solve_gpu(to, prob, opts, x0, X0, B)
+    monkeypatch.setenv("TRAJOPT_B200_SPLIT_LINESEARCH", "0")
+    fused = _solve_gpu(to, prob, opts, x0, X0, B)
+    assert split["launches"] > fused["launches"]          # the split path really ran (two more kernels per tick)
+    assert split["results"].tobytes() == fused["results"].tobytes()
+    assert np.array_equal(split["X"], fused["X"], equal_nan=True) and np.array_equal(split["U"], fused["U"], equal_nan=True)
+    for b in range(B):
+        for f in ("cost", "dJ", "gradient", "expected", "z", "rho", "alpha"):
+            assert np.array_equal(split["inner"][b][f], fused["inner"][b][f], equal_nan=True), (b, f)
+    _compare(ref, split, B)
+
+
 @pytest.mark.parametrize("name", ["pend_sqrt_altro", "dp_sqrt_ilqr", "acrobot_sqrt_al", "quad_sqrt_ilqr", "acrobot_sqrt_mintime",
                                   "dp_sqrt_mintime"])
 def test_square_root_pass_kernels_agree_bitwise(to, oracle, name, monkeypatch):

@@ -52,6 +52,8 @@ struct Variant {
     unsigned int cand_slots = 0;
     double* cand_bulk = nullptr;   // bulk candidate trajectories: trial_group per problem
     double* res_scratch = nullptr; // resident kernel: cost scratch of res_slots CTAs
+    double* split_cost = nullptr;  // split line search (tail mode, large constraint sets): knot costs of cand_slots problems
+    int* split_ok = nullptr;
     unsigned int res_slots = 0;
     double* pn_scratch = nullptr;  // projected Newton: block factors and vectors of pn_slots CTAs
     int pn_slots = 0, pn_smem = 0;
@@ -151,6 +153,10 @@ void free_variant(Variant& v) {
     if (v.cand_bulk) cudaFree(v.cand_bulk);
     if (v.res_scratch) cudaFree(v.res_scratch);
     v.res_scratch = nullptr;
+    if (v.split_cost) cudaFree(v.split_cost);
+    if (v.split_ok) cudaFree(v.split_ok);
+    v.split_cost = nullptr;
+    v.split_ok = nullptr;
     if (v.pn_scratch) cudaFree(v.pn_scratch);
     v.pn_scratch = nullptr;
     v.pn_slots = 0;
@@ -521,6 +527,20 @@ int run_lockstep_impl(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl&
         return s->fail(TO_ERR_UNSUPPORTED, "gradient_type other than :todorov needs the candidate buffers of the line search "
                                            "(not enough device memory, or TRAJOPT_B200_BULK_CANDIDATES=0)");
     const unsigned int res_threshold = (!c.o.opts_uncon.square_root && ntrial <= 32 && v.cand_alloc) ? std::min(v.res_slots * res_waves, v.cand_slots) : 0u;
+    // tail mode with large per-knot constraint sets: the cost comes off the state chain (three kernels instead of one, resident.cuh;
+    // measured on car_escape, profiles/r03a: the line search of a tick 5-7 ms -> see DESIGN section 6)
+    bool split_ls = (max_rows > 32) && v.cand_alloc && v.cand_slots > 0 && ntrial <= 32;
+    if (const char* env = getenv("TRAJOPT_B200_SPLIT_LINESEARCH")) split_ls = split_ls && (env[0] != '0');
+    if (split_ls && !v.split_cost) {
+        const size_t cost_bytes = (size_t)v.cand_slots * (size_t)s->d.N * 64 * sizeof(double);
+        if (cudaMalloc(&v.split_cost, cost_bytes) != cudaSuccess || cudaMalloc(&v.split_ok, (size_t)v.cand_slots * 32 * sizeof(int)) != cudaSuccess) {
+            cudaGetLastError();
+            if (v.split_cost) cudaFree(v.split_cost);
+            v.split_cost = nullptr;
+            v.split_ok = nullptr;
+            split_ls = false;  // not enough memory: the one-kernel line search serves
+        }
+    }
     for (long long t = 0; t < max_ticks; t++) {
         const int cur = (int)(t & 1);
         if (known_active <= res_threshold) {
@@ -579,7 +599,16 @@ int run_lockstep_impl(TOSolver* s, Variant& v, const DevBatch& Bt, const DevCtl&
         lct.cand_width = tail ? 32 : v.grids.trial_group;
         lct.cand_by_problem = tail ? 0 : 1;
         const bool with_cand = (lct.cand != nullptr);
-        if (tail) {
+        if (tail && split_ls) {
+            lct.split_cost = v.split_cost;
+            lct.split_ok = v.split_ok;
+            const unsigned long long items = (unsigned long long)known_active * (unsigned long long)s->d.N;  // one warp each, 8 per block
+            v.ki->ls_launch(LS_PHASE_SPLIT_CHAIN, v.grids, st, v.P, Bt, c, lct, cur, 0);
+            v.ki->ls_launch(LS_PHASE_SPLIT_COST, v.grids, st, v.P, Bt, c, lct, cur,
+                            (int)std::max<unsigned long long>(1, std::min<unsigned long long>((items + 7) / 8, (unsigned long long)s->sm_count * 8)));
+            v.ki->ls_launch(LS_PHASE_SPLIT_PICK, v.grids, st, v.P, Bt, c, lct, cur, 0);
+            s->launches -= ngroups - 3;
+        } else if (tail) {
             v.ki->ls_launch(LS_PHASE_TRIAL_ALL, v.grids, st, v.P, Bt, c, lct, cur, 0);
             s->launches -= ngroups - 1;
         } else {

@@ -105,10 +105,13 @@ struct LsCtl {
     int cand_width;                // step sizes per launch group (8 in the bulk, 32 in tail mode)
     int cand_by_problem;           // 1: slot = problem id (bulk buffer), 0: slot = position in the active list (tail buffer)
     double* res_scratch;           // ls_resident_kernel: per-CTA cost scratch (res_scratch_doubles(N) each)
+    double* split_cost;            // split line search (resident.cuh): [list slot][knot][stage cost x 32 | AL cost x 32]; null = off
+    int* split_ok;                 // split line search: [list slot][32] rollout stayed in the state / control box
 };
 
 constexpr int LS_BP_INLINE_RESTARTS = 2;  // regularisation increases a bulk backward-pass launch serves itself before handing the problem over
-enum { LS_PHASE_INIT = 0, LS_PHASE_JAC, LS_PHASE_BP, LS_PHASE_TRIAL, LS_PHASE_ACCEPT, LS_PHASE_OUTER, LS_PHASE_TRIAL_ALL, LS_PHASE_BP_SQRT, LS_PHASE_ACCEPT_TAIL, LS_PHASE_EXPAND, LS_PHASE_BP_CTA, LS_PHASE_RESIDENT };
+enum { LS_PHASE_INIT = 0, LS_PHASE_JAC, LS_PHASE_BP, LS_PHASE_TRIAL, LS_PHASE_ACCEPT, LS_PHASE_OUTER, LS_PHASE_TRIAL_ALL, LS_PHASE_BP_SQRT, LS_PHASE_ACCEPT_TAIL, LS_PHASE_EXPAND, LS_PHASE_BP_CTA, LS_PHASE_RESIDENT,
+       LS_PHASE_SPLIT_CHAIN, LS_PHASE_SPLIT_COST, LS_PHASE_SPLIT_PICK };
 struct LsGrids {
     int init, jac, bp, trial, accept, outer;  // grid sizes (persistent, grid-stride)
     int bp_smem, bp_groups_per_block, trial_group;

@@ -252,10 +252,16 @@ __global__ void __launch_bounds__(32) ls_init_kernel(const DevProblem P, const D
 
 // ---- outer: problems whose inner solve ended in this tick ------------------------------------
 template <class C>
-__global__ void __launch_bounds__(32) ls_outer_kernel(const DevProblem P, const DevBatch Bt, const DevCtl ctl, const LsCtl lc, const int cur) {
+__global__ void __launch_bounds__(32) ls_outer_kernel(const DevProblem Pg, const DevBatch Bt, const DevCtl ctl, const LsCtl lc, const int cur) {
     __shared__ Smem<C> sm;
+    extern __shared__ __align__(16) unsigned char ls_tab_raw[];
     const int lane = threadIdx.x;
     const unsigned int n = lc.counts[4];
+    if (blockIdx.x >= n) return;
+    // the three passes over the constraint rows (cost, violation, dual update) walk the row table: from shared memory, not as
+    // dependent global loads (car_escape, 17,900 rows per problem: 1.2 ms per tick for ONE finishing problem before)
+    DevProblem P = Pg;
+    ls_stage_problem(P, Pg, ls_tab_raw);
     for (unsigned int a = blockIdx.x; a < n; a += gridDim.x) {
         const int b = lc.outer_list[a];
         LsSolver<C> s(P, Bt, ctl, sm, lc.ws + (size_t)b * lc.ws_stride, lane);
@@ -2605,7 +2611,7 @@ template <class C> int ls_setup_fn(int sm_count, int N, int nrows, LsGrids* g) {
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_init_kernel<C>, 32, 0);
     g->init = sm_count * (nb > 0 ? nb : 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_outer_kernel<C>, 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls_outer_kernel<C>, 32, g->tab_bytes);
     g->outer = sm_count * (nb > 0 ? nb : 1);
     g->jac_pc = C::PC;
     g->jac_minb = 2;
@@ -2672,9 +2678,13 @@ template <class C> void ls_launch_fn(int phase, const LsGrids& g, cudaStream_t s
         case LS_PHASE_TRIAL: ls_trial_variant<C>(g.trial_minb, false)<<<g.trial, 128, g.tab_bytes, st>>>(P, B, c, lc, cur, grp); break;
         case LS_PHASE_TRIAL_ALL: ls_trial_variant<C>(g.trial_all_minb, true)<<<g.trial, 128, g.tab_bytes, st>>>(P, B, c, lc, cur, 0); break;
         case LS_PHASE_ACCEPT: ls_accept_kernel<C><<<g.accept, 64, 0, st>>>(P, B, c, lc, cur); break;
-        case LS_PHASE_OUTER: ls_outer_kernel<C><<<g.outer, 32, 0, st>>>(P, B, c, lc, cur); break;
+        case LS_PHASE_OUTER: ls_outer_kernel<C><<<g.outer, 32, g.tab_bytes, st>>>(P, B, c, lc, cur); break;
         case LS_PHASE_ACCEPT_TAIL: ls_accept_tail_kernel<C><<<g.outer, 32, 0, st>>>(P, B, c, lc, cur); break;
         case LS_PHASE_RESIDENT: ls_resident_variant<C>(g.res_minb)<<<grp, g.res_threads, g.res_smem, st>>>(P, B, c, lc, cur); break;
+        // split line search (tail mode, large constraint sets; resident.cuh): chains, then costs of all (knot, step size), then the pick
+        case LS_PHASE_SPLIT_CHAIN: ls_split_chain_kernel<C><<<g.trial, 128, g.tab_bytes, st>>>(P, B, c, lc, cur); break;
+        case LS_PHASE_SPLIT_COST: ls_split_cost_kernel<C><<<grp, 256, g.tab_bytes, st>>>(P, c, lc, cur); break;
+        case LS_PHASE_SPLIT_PICK: ls_split_pick_kernel<C><<<g.outer, 128, 0, st>>>(P, c, lc, cur); break;
     }
 }
 

@@ -537,4 +537,140 @@ __global__ void __launch_bounds__(NT, MINB) ls_resident_kernel(const DevProblem 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Split line search of the lockstep tick in tail mode, for problems with large per-knot constraint sets (car_escape: 177 rows).
+// ls_trial_kernel evaluates the cost ON the state chain: a thread walks 101 knots x 177 rows, 5-7 ms per tick whatever the number
+// of live problems.  Here the chain only rolls the states out and stores the candidates (the accept kernel copies the winner from
+// them anyway); the cost of every (problem, knot, step size) is then evaluated side by side from the candidates -- a warp per
+// (problem, knot), lane = step size, so the knot's rows / multipliers are broadcast loads -- and a third kernel adds the knot
+// costs up IN KNOT ORDER (the chain's own summation order: bit-identical) and picks the first accepted step size.  The same
+// decomposition as the phases T1 / T2 / T3 of ls_resident_kernel.
+template <class C>
+__global__ void __launch_bounds__(128, 3) ls_split_chain_kernel(const DevProblem Pg, const DevBatch Bt, const DevCtl ctl, const LsCtl lc,
+                                                                const int cur) {
+    extern __shared__ __align__(16) unsigned char ls_tab_raw[];
+    DevProblem P = Pg;
+    ls_stage_problem(P, Pg, ls_tab_raw);
+    __shared__ __align__(16) double stage_all[4 * 2 * RolloutStage<C>::SBUF];
+    const int* list = lc.list[cur];
+    const unsigned int na = lc.counts[cur];
+    const WsLayout L = ws_layout<C>(P.N, P.Ptot, false);
+    const bool al_on = (ctl.mode == 1);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned int per_block = blockDim.x >> 5;
+    const size_t per = cand_span((size_t)P.N * C::n, 32) + cand_span((size_t)(P.N - 1) * C::m, 32);
+    for (unsigned int a = blockIdx.x * per_block + wib; a < na; a += gridDim.x * per_block) {  // one problem per warp, lane = step size
+        const int b = list[a];
+        const LsState* st = &lc.st[b];
+        const TOiLQROptions io = ctl.o.opts_uncon;
+        const int ntrial = io.iterations_linesearch + 1;
+        const double alpha = __longlong_as_double((long long)(1023 - lane) << 52);  // 2^-lane
+        const bool runs = (st->bp_fail == 0) && lane < ntrial;
+        const unsigned amask = __ballot_sync(0xffffffffu, runs);
+        bool ok = false;
+        if (runs) {
+            double* ws = lc.ws + (size_t)b * lc.ws_stride;
+            double x0[C::n];
+#pragma unroll
+            for (int i = 0; i < C::n; i++) x0[i] = (i < C::n0) ? Bt.x0[(size_t)b * C::n0 + i] : 0.0;
+            double* XB = lc.cand + (size_t)a * per;
+            double* UB = XB + cand_span((size_t)P.N * C::n, 32);
+            double Jt;
+            ok = Rollout<C>::template run_staged<true, 32, false>(P, io, ws, L, x0, alpha, al_on, Jt, XB, UB, lane,
+                                                                  stage_all + (size_t)wib * 2 * RolloutStage<C>::SBUF, lane, __popc(amask), amask);
+        }
+        lc.split_ok[(size_t)a * 32 + lane] = ok ? 1 : 0;
+        __syncwarp();
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(256) ls_split_cost_kernel(const DevProblem Pg, const DevCtl ctl, const LsCtl lc, const int cur) {
+    constexpr int n = C::n, m = C::m;
+    extern __shared__ __align__(16) unsigned char ls_tab_raw[];
+    DevProblem P = Pg;
+    ls_stage_problem(P, Pg, ls_tab_raw);
+    const int N = P.N;
+    const unsigned int na = lc.counts[cur];
+    const WsLayout L = ws_layout<C>(N, P.Ptot, false);
+    const bool al_on = (ctl.mode == 1);
+    const int ntrial = ctl.o.opts_uncon.iterations_linesearch + 1;
+    const int t = threadIdx.x & 31;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    const unsigned long long total = (unsigned long long)na * (unsigned long long)N;
+    const size_t per = cand_span((size_t)N * n, 32) + cand_span((size_t)(N - 1) * m, 32);
+    for (unsigned long long it = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < total; it += nwarps) {
+        const unsigned int a = (unsigned int)(it / N);
+        const int k = (int)(it - (unsigned long long)a * N);
+        if (t >= ntrial || !lc.split_ok[(size_t)a * 32 + t]) continue;
+        const int b = lc.list[cur][a];
+        const double* ws = lc.ws + (size_t)b * lc.ws_stride;
+        const double* lam = ws + L.LAM;
+        const double* mu = ws + L.MU;
+        const double* XB = lc.cand + (size_t)a * per;
+        const double* UB = XB + cand_span((size_t)N * n, 32);
+        double x[n], u[m];
+#pragma unroll
+        for (int i = 0; i < n; i++) x[i] = XB[cand_index((size_t)k * n + i, t, 32)];
+        double cs, ca = 0.0;
+        if (k < N - 1) {
+#pragma unroll
+            for (int i = 0; i < m; i++) u[i] = UB[cand_index((size_t)k * m + i, t, 32)];
+            cs = stage_cost<C>(P, x, u);
+            if (al_on) {
+                const int lo = P.knot_lam_off[k];
+                ca = knot_al_cost_at<C>(P, k, lam + lo, mu + lo, x, u);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < m; i++) u[i] = 0.0;
+            cs = term_cost<C>(P, x);
+            if (al_on) ca = knot_al_cost<C>(P, N - 1, lam, mu, x, u);
+        }
+        double* out = lc.split_cost + ((size_t)a * N + k) * 64;
+        out[t] = cs;
+        out[32 + t] = ca;
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(128) ls_split_pick_kernel(const DevProblem P, const DevCtl ctl, const LsCtl lc, const int cur) {
+    const int N = P.N;
+    const unsigned int na = lc.counts[cur];
+    const bool al_on = (ctl.mode == 1);
+    const int lane = threadIdx.x & 31;
+    const unsigned int per_block = blockDim.x >> 5;
+    for (unsigned int a = blockIdx.x * per_block + (threadIdx.x >> 5); a < na; a += gridDim.x * per_block) {
+        const int b = lc.list[cur][a];
+        LsState* st = &lc.st[b];
+        if (st->bp_fail != 0) continue;  // backward pass aborted: no line search for this problem
+        const TOiLQROptions io = ctl.o.opts_uncon;
+        const int ntrial = io.iterations_linesearch + 1;
+        const double alpha = __longlong_as_double((long long)(1023 - lane) << 52);
+        bool accept = false;
+        double Jt = 0.0, expected = 0.0, z = 0.0;
+        if (lane < ntrial && lc.split_ok[(size_t)a * 32 + lane]) {
+            const double* c = lc.split_cost + (size_t)a * N * 64;
+            double J = 0.0, Jc = 0.0;
+#pragma unroll 4
+            for (int k = 0; k < N; k++) J += c[(size_t)k * 64 + lane];
+            if (al_on) {
+#pragma unroll 4
+                for (int k = 0; k < N; k++) Jc += c[(size_t)k * 64 + 32 + lane];
+            }
+            Jt = al_on ? (J + Jc) : J;
+            const double dV0 = st->dV0, dV1 = st->dV1, J_prev = st->J_prev;
+            expected = -alpha * (dV0 + alpha * dV1);
+            z = (expected > 0) ? (J_prev - Jt) / expected : -1.0;
+            const bool cont = (z <= io.line_search_lower_bound || z > io.line_search_upper_bound) && (Jt >= J_prev);
+            accept = !cont;
+        }
+        const unsigned msk = __ballot_sync(0xffffffffu, accept);
+        if (msk != 0 && lane == __ffs(msk) - 1) {
+            st->winner = lane;
+            st->Jres = Jt; st->exp_res = expected; st->z_res = z;
+        }
+    }
+}
+
 }  // namespace tob
