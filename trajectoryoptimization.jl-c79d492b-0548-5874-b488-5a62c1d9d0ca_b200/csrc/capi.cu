@@ -392,7 +392,9 @@ int ensure_engine_buffers(TOSolver* s, Variant& v) {
         if (slots > 0 && cudaMalloc(&v.cand_alloc, (size_t)slots * per * sizeof(double)) == cudaSuccess) v.cand_slots = slots;
         else { cudaGetLastError(); v.cand_alloc = nullptr; v.cand_slots = 0; }
         // bulk: the G candidates of every problem (skipped if it would not leave a quarter of the device memory free)
-        const size_t bulk_bytes = B * (per / 32) * (size_t)v.grids.trial_group * sizeof(double);
+        // (4-component chunks per knot: cand_chunk_span in lockstep.cuh)
+        const size_t bulk_per = ((size_t)N * (size_t)((v.ki->n + 3) / 4) + (size_t)(N - 1) * (size_t)((v.ki->m + 3) / 4)) * 4 * (size_t)v.grids.trial_group;
+        const size_t bulk_bytes = B * bulk_per * sizeof(double);
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         const char* env = getenv("TRAJOPT_B200_BULK_CANDIDATES");

@@ -1989,6 +1989,26 @@ TOB_DEV double knot_al_cost_at(const DevProblem& P, int k, const double* lamk, c
 // 3.17 -> 3.54 ms.  Kept element-wise.)
 __host__ __device__ __forceinline__ size_t cand_index(size_t e, int col, int CW) { return e * (size_t)CW + (size_t)col; }
 __host__ __device__ __forceinline__ size_t cand_span(size_t count, int CW) { return count * (size_t)CW; }  // doubles for `count` elements
+// Bulk candidates (CW = LS_TRIAL_G step sizes per problem): [knot][chunk of 4 components][step size][4 doubles].  A thread of the
+// line search writes whole 32-byte sectors (its 4-component chunk), the 8 step sizes of a problem side by side (256 contiguous
+// bytes), and the accept kernel reads exactly the winner's sectors.  The element-interleaved layout ([element][step size], kept
+// for the 32-wide tail / resident buffers, which live in L2) made that read fetch 4x what it used: one 8-byte column out of every
+// 32-byte sector, 1.07 GB for 0.27 GB per tick of 8,192 problems.
+__host__ __device__ __forceinline__ int cand_chunks(int comps) { return (comps + 3) >> 2; }
+__host__ __device__ __forceinline__ size_t cand_chunk_span(size_t knots, int comps, int CW) { return knots * (size_t)cand_chunks(comps) * (size_t)CW * 4; }
+__host__ __device__ __forceinline__ size_t cand_chunk_index(size_t k, int chunk, int comps, int slot, int CW) {
+    return ((k * (size_t)cand_chunks(comps) + (size_t)chunk) * (size_t)CW + (size_t)slot) * 4;
+}
+// store comps doubles of knot k as 4-component chunks (zero padded)
+template <int COMPS>
+__device__ __forceinline__ void cand_store_chunks(double* base, size_t k, int slot, int CW, const double* v) {
+#pragma unroll
+    for (int c = 0; c < (COMPS + 3) / 4; c++) {
+        double2* dst = reinterpret_cast<double2*>(base + cand_chunk_index(k, c, COMPS, slot, CW));
+        dst[0] = make_double2(v[4 * c], (4 * c + 1 < COMPS) ? v[4 * c + 1] : 0.0);
+        dst[1] = make_double2((4 * c + 2 < COMPS) ? v[4 * c + 2] : 0.0, (4 * c + 3 < COMPS) ? v[4 * c + 3] : 0.0);
+    }
+}
 
 
 template <class C>
@@ -2062,10 +2082,15 @@ struct Rollout {
                 Jc += knot_al_cost_at<C>(P, k, staged ? (sk + SS) : (lam + lo), staged ? (sk + SS + LC) : (mu + lo), xb, ub);
             }
             if (CAND) {
+                if constexpr (CW == 32) {
 #pragma unroll
-                for (int i = 0; i < n; i++) XB[cand_index((size_t)k * n + i, slot, CW)] = xb[i];
+                    for (int i = 0; i < n; i++) XB[cand_index((size_t)k * n + i, slot, CW)] = xb[i];
 #pragma unroll
-                for (int i = 0; i < m; i++) UB[cand_index((size_t)k * m + i, slot, CW)] = ub[i];
+                    for (int i = 0; i < m; i++) UB[cand_index((size_t)k * m + i, slot, CW)] = ub[i];
+                } else {
+                    cand_store_chunks<n>(XB, (size_t)k, slot, CW, xb);
+                    cand_store_chunks<m>(UB, (size_t)k, slot, CW, ub);
+                }
             }
             double xn[n];
             {
@@ -2098,8 +2123,12 @@ struct Rollout {
             if (COST) J += term_cost<C>(P, xb);
             if (COST && al_on) Jc += knot_al_cost<C>(P, N - 1, lam, mu, xb, uz);
             if (CAND) {
+                if constexpr (CW == 32) {
 #pragma unroll
-                for (int i = 0; i < n; i++) XB[cand_index((size_t)(N - 1) * n + i, slot, CW)] = xb[i];
+                    for (int i = 0; i < n; i++) XB[cand_index((size_t)(N - 1) * n + i, slot, CW)] = xb[i];
+                } else {
+                    cand_store_chunks<n>(XB, (size_t)(N - 1), slot, CW, xb);
+                }
             }
         }
         __syncwarp(amask);  // nobody reads the staging buffers any more
@@ -2254,9 +2283,10 @@ __global__ void __launch_bounds__(128, MINB) ls_trial_kernel(const DevProblem Pg
             if (lc.cand != nullptr) {
                 // keep every candidate of this group: G-way interleaved, slot = problem id (bulk) or list position (tail),
                 // column = step size within the group; the accept kernel copies the winner instead of re-rolling it
-                const size_t per = cand_span((size_t)P.N * C::n, G) + cand_span((size_t)(P.N - 1) * C::m, G);
-                double* XB = lc.cand + (size_t)(lc.cand_by_problem ? (unsigned int)b : a0) * per;
-                double* UB = XB + cand_span((size_t)P.N * C::n, G);
+                const size_t xspan = (G == 32) ? cand_span((size_t)P.N * C::n, G) : cand_chunk_span((size_t)P.N, C::n, G);
+                const size_t uspan = (G == 32) ? cand_span((size_t)(P.N - 1) * C::m, G) : cand_chunk_span((size_t)(P.N - 1), C::m, G);
+                double* XB = lc.cand + (size_t)(lc.cand_by_problem ? (unsigned int)b : a0) * (xspan + uspan);
+                double* UB = XB + xspan;
                 ok = Rollout<C>::template run_staged<true, G>(P, io, ws, L, x0, alpha, al_on, Jt, XB, UB, t, stg, t, nact, amask);
             } else {
                 ok = Rollout<C>::template run_staged<false, G>(P, io, ws, L, x0, alpha, al_on, Jt, nullptr, nullptr, 0, stg, t, nact, amask);
@@ -2322,14 +2352,43 @@ __global__ void __launch_bounds__(32) ls_accept_tail_kernel(const DevProblem P, 
                 if (!err && !(Jres > s.io.max_cost_value)) {
                     const int W = lc.cand_width, col = w % W;
                     const int nx = N * C::n, nu = (N - 1) * C::m;
-                    const size_t per = cand_span((size_t)nx, W) + cand_span((size_t)nu, W);
-                    const double* XB = lc.cand + (size_t)(lc.cand_by_problem ? (unsigned int)b : a) * per;
-                    const double* UB = XB + cand_span((size_t)nx, W);
-                    // (unrolled: 8 independent loads in flight per lane -- the copy is a DRAM-latency chain otherwise)
+                    if (W == 32) {  // tail buffer: element-interleaved
+                        const size_t per = cand_span((size_t)nx, W) + cand_span((size_t)nu, W);
+                        const double* XB = lc.cand + (size_t)(lc.cand_by_problem ? (unsigned int)b : a) * per;
+                        const double* UB = XB + cand_span((size_t)nx, W);
+                        // (unrolled: 8 independent loads in flight per lane -- the copy is a DRAM-latency chain otherwise)
 #pragma unroll 8
-                    for (int e = lane; e < nx; e += 32) s.ws[s.L.X + e] = XB[cand_index((size_t)e, col, W)];
+                        for (int e = lane; e < nx; e += 32) s.ws[s.L.X + e] = XB[cand_index((size_t)e, col, W)];
 #pragma unroll 8
-                    for (int e = lane; e < nu; e += 32) s.ws[s.L.U + e] = UB[cand_index((size_t)e, col, W)];
+                        for (int e = lane; e < nu; e += 32) s.ws[s.L.U + e] = UB[cand_index((size_t)e, col, W)];
+                    } else {        // bulk buffer: 4-component chunks, one 32-byte sector of the winner per lane and load pair
+                        constexpr int XC = (C::n + 3) / 4, UC = (C::m + 3) / 4;
+                        const size_t xspan = cand_chunk_span((size_t)N, C::n, W), uspan = cand_chunk_span((size_t)(N - 1), C::m, W);
+                        const double* XB = lc.cand + (size_t)(lc.cand_by_problem ? (unsigned int)b : a) * (xspan + uspan);
+                        const double* UB = XB + xspan;
+#pragma unroll 4
+                        for (int q = lane; q < N * XC; q += 32) {
+                            const int k = q / XC, c = q - k * XC;
+                            const double2* src = reinterpret_cast<const double2*>(XB + cand_chunk_index((size_t)k, c, C::n, col, W));
+                            const double2 v0 = src[0], v1 = src[1];
+                            double* dst = s.ws + s.L.X + (size_t)k * C::n + 4 * c;
+                            dst[0] = v0.x;
+                            if (4 * c + 1 < C::n) dst[1] = v0.y;
+                            if (4 * c + 2 < C::n) dst[2] = v1.x;
+                            if (4 * c + 3 < C::n) dst[3] = v1.y;
+                        }
+#pragma unroll 4
+                        for (int q = lane; q < (N - 1) * UC; q += 32) {
+                            const int k = q / UC, c = q - k * UC;
+                            const double2* src = reinterpret_cast<const double2*>(UB + cand_chunk_index((size_t)k, c, C::m, col, W));
+                            const double2 v0 = src[0], v1 = src[1];
+                            double* dst = s.ws + s.L.U + (size_t)k * C::m + 4 * c;
+                            dst[0] = v0.x;
+                            if (4 * c + 1 < C::m) dst[1] = v0.y;
+                            if (4 * c + 2 < C::m) dst[2] = v1.x;
+                            if (4 * c + 3 < C::m) dst[3] = v1.y;
+                        }
+                    }
                     __syncwarp();
                 }
             } else {
