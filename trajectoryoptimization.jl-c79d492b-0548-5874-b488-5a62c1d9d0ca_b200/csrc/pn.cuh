@@ -19,6 +19,7 @@ namespace tob {
 
 constexpr int LS_PN_PA = 24;  // active constraint rows of one knot the block factor holds (a knot with more -> TO_STATUS_PN_SKIPPED)
 constexpr int LS_PN_THREADS = 128;
+constexpr int LS_PN_MINB = 4;  // 128 registers, four CTAs per SM: the kernel is a latency chain per problem (profiles/r03f_pn_throughput.log: 2 / 4 / 5 / 6 CTAs per SM -> polish of 8,192 quadrotor problems 2,201 / 1,229 / 1,375 / 1,809 ms)
 
 template <class C> struct PnDims {
     static constexpr int n = C::n, m = C::m;
@@ -507,7 +508,7 @@ struct PnOptsDev {
 };
 
 template <class C>
-__global__ void __launch_bounds__(LS_PN_THREADS) ls_pn_kernel(const DevProblem Pg, const DevBatch Bt, const LsCtl lc, const PnOptsDev po,
+__global__ void __launch_bounds__(LS_PN_THREADS, LS_PN_MINB) ls_pn_kernel(const DevProblem Pg, const DevBatch Bt, const LsCtl lc, const PnOptsDev po,
                                                            double* scratch, const unsigned long long scratch_stride) {
     constexpr int n = C::n, m = C::m, NT = LS_PN_THREADS;
     extern __shared__ __align__(16) unsigned char pn_smem_raw[];
